@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py -- rotations/s of the fused Fisher NLL + gradient + entropy + percentile filter.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric, config 5 sharded): every GPU owns 2^23 synthetic (A, R_gt)
+pairs (2^26 at 8 GPUs).  One step = one pass of the hot path over that pool:
+  K2  fused matrix-Fisher kernel -> NLL, d NLL/dA, entropy, first radix histogram
+  K3  global percentile threshold (k = int(n_total * 0.95)): 2 more histogram passes,
+      3 scans; on N > 1 GPUs the 2048-bin histograms are all-gathered over NCCL
+  K3  keep-mask emit (entropy < threshold)
+Inputs are resident in HBM for `value`; `e2e` runs the same step through the C ABI's
+host-buffer entry (pinned host inputs, H2D and D2H copies inside the timed region).
+`--impl reference` times the reference's CPU algorithm (oracle port: torch CPU, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rotations/sec fused Fisher NLL+grad+entropy+filter"
+UNIT = "rotations/s"
+N_PER_GPU = 1 << 23
+LEFT_RATIO = 0.95
+OVERREG = 1.025
+FLOP_PER_ROTATION = 69120          # 3 families x 512 nodes x 45 FLOP
+HBM_BYTES_PER_ROTATION = 36 + 36 + 4 + 36 + 4   # A, R in; nll, grad, entropy out (K2)
+CPU_SAMPLE = 1 << 16
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = str(gpu_index)
+        self.proc, self.rows = None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------ CPU baseline
+def cpu_step(orc, torch, np, A, R):
+    """The reference's CPU algorithm for one step on a sample: vmf_loss fwd+bwd (agent.py:79,209),
+    fisher_entropy (agent.py:139), sort/index threshold + strict-< mask (agent.py:403-407,148)."""
+    leaf = A.clone().requires_grad_(True)
+    loss, _ = orc.vmf_loss(leaf, R, overreg=OVERREG)
+    loss.mean().backward()
+    with torch.no_grad():
+        ent = orc.fisher_entropy(A)
+    thr, _ = orc.pool_threshold(ent.numpy(), LEFT_RATIO)
+    mask, _ = orc.keep_mask(ent, float(thr))
+    return float(loss.detach().mean()), int(mask.sum())
+
+
+def synth_cpu(torch, n, seed):
+    gen = torch.Generator().manual_seed(seed)
+    A = 10 * torch.randn(n, 9, generator=gen)
+    q = torch.randn(n, 4, generator=gen)
+    q = q / q.norm(dim=1, keepdim=True)
+    from oracle import pytorch3d_restated as p3d
+    return A, p3d.quaternion_to_matrix(q).contiguous()
+
+
+def pick_threads(orc, torch, np):
+    """The reference arm gets the thread count it runs fastest with on this host (on
+    oversubscribed VMs torch's OpenMP pool can be slower at cpu_count() than at 2)."""
+    cores = os.cpu_count() or 1
+    A, R = synth_cpu(torch, 512, 99)
+    best_t, best_n = None, cores
+    n = cores
+    while n >= 1:
+        torch.set_num_threads(n)
+        cpu_step(orc, torch, np, A[:64], R[:64])
+        t0 = time.perf_counter()
+        cpu_step(orc, torch, np, A, R)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_t, best_n = dt, n
+        n //= 2
+    torch.set_num_threads(best_n)
+    return best_n
+
+
+def time_cpu(sample, repeats):
+    import numpy as np
+    import torch
+    from oracle import so3_oracle as orc
+    cores = pick_threads(orc, torch, np)
+    A, R = synth_cpu(torch, sample, 1234)
+    cpu_step(orc, torch, np, A[:256], R[:256])            # warm-up
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_step(orc, torch, np, A, R)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample / best, cores, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import so3_oracle as orc
+    cores = pick_threads(orc, torch, np)
+    sample = max(args.cpu_sample // 4, 1024)          # per step; K steps stay within a few minutes
+    A, R = synth_cpu(torch, sample, 1234)
+    for _ in range(max(args.warmup, 1)):
+        cpu_step(orc, torch, np, A[:2048], R[:2048])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(orc, torch, np, A, R)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, args.n_per_gpu),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
+                         "sample": f"{sample} of the pool's rotations per step: oracle/so3_oracle.py (torch CPU restatement "
+                                   "of vmf_loss fwd+bwd, fisher_entropy, numpy sort threshold, mask), all host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, n_per_gpu):
+    return {"workload": f"BASELINE config 5 sharded: {n_per_gpu} synthetic (A=10*randn, R_gt random rotation) pairs per GPU "
+                        f"({n_per_gpu * n_gpus} total), Fisher NLL+grad+entropy (overreg={OVERREG}) + global percentile "
+                        f"filter left_ratio={LEFT_RATIO}",
+            "rotations_per_gpu": n_per_gpu, "rotations_total": n_per_gpu * n_gpus, "left_ratio": LEFT_RATIO,
+            "parallelism": f"batch-sharded x{n_gpus}, all-gather of 2048-bin radix histograms",
+            "l2": "inputs (604 MB per GPU) exceed the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        graft.build()
+    if world > 1:
+        dist.barrier()
+    from semiuhpe_b200 import _capi, _ops
+    import semiuhpe_b200
+    from semiuhpe_b200.agent import pool_index, _quat_to_matrix
+    from semiuhpe_b200.distributed import CudaHistogramBackend
+    semiuhpe_b200.set_error_checking(False)          # sync-free steps; finiteness is asserted after the run
+    lib = _capi.lib()
+
+    n = args.n_per_gpu
+    n_total = n * world
+    k = pool_index(n_total, LEFT_RATIO)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    A = 10 * torch.randn(n, 9, device=dev, generator=gen)
+    q = torch.randn(n, 4, device=dev, generator=gen)
+    R = _quat_to_matrix(q / q.norm(dim=1, keepdim=True)).reshape(n, 9).contiguous()
+    del q
+    new = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)
+    nll, grad, ent, mask = new(n), new(n, 9), new(n), new(n, dt=torch.bool)
+    ws = _ops.SelectWorkspace(dev)
+    kept = torch.zeros(1, dtype=torch.int64, device=dev)
+    gathered = torch.empty((world, _capi.HIST_BINS), dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    P, S = _capi.ptr, _capi.stream
+    launches = [0]
+
+    def fused():
+        _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, OVERREG, P(nll), P(grad), None, P(ent), None, None, None,
+                                               P(ws.hist[0]), P(status), S()), "fused")
+        launches[0] += 1
+
+    def step():
+        ws.hist.zero_()
+        kept.zero_()
+        fused()
+        _capi.check(lib.suhpe_select_init(P(ws.state), k, S()), "init"); launches[0] += 1
+        for p in (1, 2, 3):
+            if p == 1:
+                local_hist = ws.hist[0]
+            else:
+                local_hist = ws.hist[1]
+                _capi.check(lib.suhpe_select_hist_f32(P(ent), n, p, P(ws.state), P(local_hist), S()), "hist")
+                launches[0] += 1
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, local_hist.reshape(1, -1))
+                src, parts = gathered, world
+            else:
+                src, parts = local_hist, 1
+            _capi.check(lib.suhpe_select_scan(P(src), parts, p, P(ws.state), S()), "scan"); launches[0] += 1
+        _capi.check(lib.suhpe_entropy_mask_f32(P(ent), n, ws.threshold_ptr(), 0.0, P(mask), P(kept), S()), "mask")
+        launches[0] += 1
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    step_launches = launches[0]
+
+    # dominant kernel alone (same stream, CUDA events): roofline numerator
+    for _ in range(3):
+        fused()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(args.steps, 5)
+    k0.record()
+    for _ in range(reps):
+        fused()
+    k1.record()
+    torch.cuda.synchronize()
+    fused_ms = k0.elapsed_time(k1) / reps
+    clocks = sampler.stop() if sampler else None
+
+    thr, _, kept_n = ws.read()
+    assert int(status.item()) == 0 and bool(torch.isfinite(nll).all()) and bool(torch.isfinite(ent).all())
+    value = n_total * args.steps / (ms_total * 1e-3)
+
+    # end-to-end leg on every rank at once (they share the host's PCIe/memory system), max over ranks
+    e2e = run_e2e(torch, dist, dev, n, args, world, rank)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 extras -------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    probe = fp32_probe(torch, lib, dev, _capi)
+    achieved_tflops = n * FLOP_PER_ROTATION / (fused_ms * 1e-3) / 1e12
+    peak_tflops = max(probe["ffma_tflops"], probe["ffma2_tflops"])
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_gbs = n * HBM_BYTES_PER_ROTATION / (fused_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "fp32", "kernel": "fisher_fused_kernel", "achieved": achieved_tflops, "peak": peak_tflops,
+        "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
+        "peak_source": "FP32 FMA micro-benchmark run on this GPU in this process (suhpe_fp32_probe; MEASURED_PEAKS.json "
+                       "has no FP32-pipe figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+        "algorithmic_flop_per_rotation": FLOP_PER_ROTATION, "rotations_per_launch": n, "kernel_ms": fused_ms,
+        "kernel_share_of_step": fused_ms / (ms_total / args.steps),
+        "traffic": None,
+        "hbm_view": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
+                     "bytes_per_rotation": HBM_BYTES_PER_ROTATION,
+                     "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback"},
+        "probe": probe,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world, n),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": step_launches, "roofline": roofline,
+        "threshold": thr, "kept": kept_n,
+    }
+    if world == 1:
+        v, cores, secs = time_cpu(args.cpu_sample, 1)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{args.cpu_sample} rotations of the same workload, 1 pass ({secs:.1f} s): oracle/so3_oracle.py "
+                      "(torch-CPU restatement of the reference: vmf_loss fwd+bwd, fisher_entropy, numpy sort + mask), "
+                      "all host threads"}
+        if not args.skip_extra:
+            line["extra"] = side_configs(torch, dev, _ops)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
+def fp32_probe(torch, lib, dev, _capi):
+    """FP32-pipe peak on this GPU: 8 independent FMA chains per thread, 148*8 CTAs x 256 threads."""
+    sink = torch.zeros(4, device=dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, iters = sms * 8, 4096
+    out = {}
+    for variant, name, per in ((0, "ffma", 1), (1, "ffma2", 2), (2, "ffma_mufu", 1)):
+        for _ in range(2):
+            _capi.check(lib.suhpe_fp32_probe(_capi.ptr(sink), variant, iters, blocks, _capi.stream()), "probe")
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            _capi.check(lib.suhpe_fp32_probe(_capi.ptr(sink), variant, iters, blocks, _capi.stream()), "probe")
+        b.record()
+        torch.cuda.synchronize()
+        fmas = 3.0 * blocks * 256 * iters * 64 * per
+        out[name + "_tflops"] = 2 * fmas / (a.elapsed_time(b) * 1e-3) / 1e12
+    return out
+
+
+def run_e2e(torch, dist, dev, n, args, world, rank):
+    """Same step through the C ABI's host-buffer entry: pinned host A/R -> H2D -> K2/K3 -> D2H."""
+    from semiuhpe_b200.host_pipeline import FisherFilterPipeline
+    gen = torch.Generator().manual_seed(77 + rank)
+    A_h = (10 * torch.randn(n, 9, generator=gen)).pin_memory()
+    q = torch.randn(n, 4, generator=gen)
+    q = q / q.norm(dim=1, keepdim=True)
+    from semiuhpe_b200.agent import _quat_to_matrix
+    R_h = _quat_to_matrix(q).reshape(n, 9).contiguous().pin_memory()
+    pipe = FisherFilterPipeline(max_n=n, chunk=1 << 20, device=dev.index)
+    res = pipe.run(A_h, R_h, OVERREG, LEFT_RATIO)          # warm-up (allocates pinned outputs)
+    pipe.run(A_h, R_h, OVERREG, LEFT_RATIO)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = pipe.run(A_h, R_h, OVERREG, LEFT_RATIO)      # blocking call: results are on the host on return
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out = {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": res["h2d_bytes"],
+           "d2h_bytes_per_step": res["d2h_bytes"], "steps": steps, "ms_per_step": 1e3 * dt / steps,
+           "api": "semiuhpe_b200.host_pipeline.FisherFilterPipeline.run -> suhpe_fisher_filter_host (1 Mi-pair chunks, 2 streams)",
+           "note": "all ranks concurrently, max over ranks; the threshold in this leg is per-rank" if world > 1 else "single GPU"}
+    pipe.close()
+    return out
+
+
+def side_configs(torch, dev, _ops):
+    """Device-timed side numbers for BASELINE configs 1-4 (parity-test cases, reported for context)."""
+    import semiuhpe_b200
+    from semiuhpe_b200.agent import dynamic_entropy_filter, _quat_to_matrix
+    from semiuhpe_b200.fisher.fisher_utils import vmf_loss
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    gen = torch.Generator(device=dev).manual_seed(5)
+    rot = lambda m: _quat_to_matrix(torch.nn.functional.normalize(torch.randn(m, 4, device=dev, generator=gen), dim=1)).contiguous()
+    A32, R32 = 10 * torch.randn(32, 9, device=dev, generator=gen), rot(32)
+    A128 = 10 * torch.randn(128, 9, device=dev, generator=gen)
+
+    def c1():
+        leaf = A32.clone().requires_grad_(True)
+        loss, _ = vmf_loss(leaf, R32, overreg=OVERREG)
+        loss.mean().backward()
+
+    def c2():
+        c1()
+        dynamic_entropy_filter(A128, LEFT_RATIO, return_threshold=False)
+
+    out["c1_fisher_b32_fwd_bwd_us"] = 1e3 * timed(c1, 50)
+    out["c2_teacher_step_32_128_us"] = 1e3 * timed(c2, 50)
+    n3, N = 1 << 20, 4608
+    grid = rot(N)
+    A3, R3 = 5 * torch.randn(n3, 9, device=dev, generator=gen), rot(n3)
+    ms = timed(lambda: _ops.laplace_nll(A3, R3, grid, grad=True, mode=True), 3)
+    out["c3_laplace_2p20_N4608_ms"] = ms
+    out["c3_laplace_rot_per_s"] = n3 / (ms * 1e-3)
+    out["c3_laplace_tflops_at_230400_flop"] = n3 * 230400 / (ms * 1e-3) / 1e12
+    n4 = 10_000_000
+    Rp, Rg = rot(n4), rot(n4)
+    ge = (torch.rand(n4, 3, device=dev, generator=gen) * 2 - 1) * 89
+    ms = timed(lambda: _ops.so3_metrics(Rp, Rg, ge, geo=True, frob=True, abs_err=True, sums=True), 5)
+    out["c4_metrics_10M_ms"] = ms
+    out["c4_metrics_gbs_at_104B"] = n4 * 104 / (ms * 1e-3) / 1e9
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--skip-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

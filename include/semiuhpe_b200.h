@@ -1,0 +1,129 @@
+/* semiuhpe_b200.h -- C ABI of the B200-native rotation-distribution hot path.
+ *
+ * One shared library (libsemiuhpe_b200.so, built for sm_100a by
+ * __graft_entry__.build()) exports exactly these symbols.  Plain pointers and
+ * sizes only; device pointers unless the function name ends in `_host`.
+ * Every function returns 0 on success, -(cudaError_t) for a CUDA failure and
+ * SUHPE_EINVAL for a bad argument; nothing throws and nothing synchronises the
+ * device except the `_host` pipeline and suhpe_select_read.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * The reference (hnuzhy/SemiUHPE) has no FFI: the path sits behind plain Python
+ * functions.  Each entry point names the reference function(s) it replaces
+ * (paths relative to the reference root); semiuhpe_b200/*.py mirrors those
+ * Python signatures on top of this ABI and INTEGRATION.md shows the binding.
+ *
+ * Records: a rotation / parameter matrix is 9 contiguous fp32 (row-major 3x3).
+ */
+#ifndef SEMIUHPE_B200_H
+#define SEMIUHPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUHPE_ABI_VERSION 1
+#define SUHPE_EINVAL (-100000)
+
+/* bits OR-ed into the optional device `status` word */
+#define SUHPE_STATUS_NONFINITE   1  /* A held NaN/Inf: torch.svd raises there (fisher_utils.py:28) */
+#define SUHPE_STATUS_TRACE_RANGE 2  /* trace(R1 R2^T) out of [-1-1e-4, 3+1e-4]: pytorch3d raises ValueError */
+
+#define SUHPE_HIST_BINS 2048        /* uint64 counters per radix histogram */
+#define SUHPE_SELECT_STATE_BYTES 32 /* opaque device block, see suhpe_select_read */
+
+int suhpe_abi_version(void);
+const char* suhpe_error_string(int code);
+
+/* K1 -- proper SVD projection onto SO(3):  A = U diag(S) V^T, det U = det V = +1,
+ * S0 >= S1 >= |S2| (S2 signed), R = U V^T.
+ * Replaces batch_torch_A_to_R (src/fisher/fisher_utils.py:39-48), analytical_mode
+ * (src/laplace/rotation_laplace.py:102-115) and proper_svd
+ * (src/fisher/between_bingham_fisher.py:63-82).  R,S,U,V,status nullable. */
+int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U, float* V,
+                         int* status, void* stream);
+
+/* K2 -- fused matrix-Fisher head: per sample
+ *   nll     = -<A,Rgt> + overreg * logC(S)                 KL_Fisher   fisher_utils.py:21-36
+ *   grad    = d nll / dA = -Rgt + overreg * U diag(g) V^T  class_logC_F.backward torch_norm_factor.py:80-90
+ *   Rout    = U V^T                                        batch_torch_A_to_R fisher_utils.py:39-48
+ *   entropy = log f(S) + sum_j S_j (1 - g_j)               fisher_entropy fisher_utils.py:70-81
+ *   logC, S (n,3), G = dlogC/dS (n,3)                      logC_F torch_norm_factor.py:66-92
+ *   hist   += histogram of the top 11 bits of the entropy keys (first radix-select pass, fused)
+ * Rgt may be NULL (then nll = overreg*logC and grad has no -Rgt term); every output is nullable. */
+int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg,
+                           float* nll, float* grad, float* Rout, float* entropy, float* logC,
+                           float* S, float* G, uint64_t* hist, int* status, void* stream);
+
+/* K2 on given singular values: logC_F(S) and its backward G = dlogC/dS, entropy(S)
+ * (src/fisher/torch_norm_factor.py:66-92 `logC_F`; S (n,3) sorted s1>=s2>=|s3| like every
+ * reference call site).  Outputs nullable. */
+int suhpe_fisher_from_s_f32(const float* S, int64_t n, float* logC, float* G, float* entropy,
+                            int* status, void* stream);
+
+/* K2L -- rotation-Laplace NLL forward+backward against an SO(3) grid (N,9), device resident.
+ * Replaces NLL_loss("RLaplace") / log_pdf / logF_const_laplace / power_fn_sqrtL2_proper /
+ * analytical_mode (src/laplace/rotation_laplace.py:24-34,58-115,140-173) and their autograd
+ * backward.  grad, mode, logF, status nullable. */
+int suhpe_laplace_nll_f32(const float* A, const float* Rgt, int64_t n, const float* grid, int32_t N,
+                          float* nll, float* grad, float* mode, float* logF, int* status, void* stream);
+
+/* K3 -- dynamic-entropy filter (src/agent.py:148-150,403-407).
+ * Exact k-th smallest (0-based rank k in numpy.sort order: ascending, -0==+0, NaN last)
+ * by three radix passes.  Single GPU: suhpe_entropy_threshold_f32 chains everything on
+ * `stream`.  Multi GPU: call suhpe_select_init, then per pass p=1,2,3
+ * suhpe_select_hist (local shard) -> all-gather the SUHPE_HIST_BINS counters of every rank
+ * (NCCL) -> suhpe_select_scan over the gathered (parts,SUHPE_HIST_BINS) block.
+ * `state` is SUHPE_SELECT_STATE_BYTES of device memory; `hist` SUHPE_HIST_BINS uint64. */
+int suhpe_select_init(void* state, uint64_t k, void* stream);
+int suhpe_select_hist_f32(const float* entropy, int64_t n, int32_t pass, const void* state,
+                          uint64_t* hist, void* stream);
+int suhpe_select_scan(const uint64_t* hist_parts, int32_t parts, int32_t pass, void* state, void* stream);
+/* first_pass_hist: optional histogram already produced by suhpe_fisher_fused_f32 (skips pass 1's read) */
+int suhpe_entropy_threshold_f32(const float* entropy, int64_t n, uint64_t k, void* state,
+                                uint64_t* hist_scratch, const uint64_t* first_pass_hist, void* stream);
+/* device pointer to the fp32 threshold inside `state` (valid after pass 3) */
+const float* suhpe_select_threshold_ptr(const void* state);
+/* blocking read-back of the state block: threshold, its key, kept count */
+int suhpe_select_read(const void* state, float* threshold, uint32_t* key, uint64_t* kept, void* stream);
+/* mask[i] = entropy[i] < thr  (thr read from thr_dev if non-NULL, else thr_host); kept += popcount.
+ * mask nullable (count only); kept nullable. */
+int suhpe_entropy_mask_f32(const float* entropy, int64_t n, const float* thr_dev, float thr_host,
+                           uint8_t* mask, uint64_t* kept, void* stream);
+
+/* K4 -- error metrics over rotation pairs.
+ *   geo_deg  rad2deg(so3_relative_angle(Rp,Rg))       src/agent.py:449-451, eval.py:88-89
+ *   frob     ||I - Rp Rg^T||_F                        eval.py:93-98
+ *   euler    (pitch,yaw,roll) radians of Rp           src/utils.py:232-260
+ *   abs_err  |euler*180/pi - gt_euler|, mae = mean_3  src/agent.py:452-454, eval.py:76-83
+ *   sums[8] += {geo, frob, |dpitch|, |dyaw|, |droll|, mae, 0, 0} in fp64 (eval.py:125-133 means)
+ * Rg may be NULL when only Euler angles are wanted; all outputs nullable. */
+int suhpe_so3_metrics_f32(const float* Rp, const float* Rg, const float* gt_euler_deg, int64_t n,
+                          int32_t full_range, float* geo_deg, float* frob, float* euler,
+                          float* abs_err, float* mae, double* sums, int* status, void* stream);
+
+/* FP32-pipe probe used by bench.py for the roofline denominator: launches `blocks` CTAs of
+ * 256 threads, each thread running `iters` rounds of 8 independent dependent-FMA chains.
+ * variant 0: scalar FFMA, 1: packed fma.rn.f32x2, 2: FFMA + 1 MUFU.EX2 per 8 FMA.
+ * FMAs executed = blocks*256*iters*8*(variant==1 ? 2 : 1) * 8 (unroll). */
+int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks, void* stream);
+
+/* Host-buffer pipeline (what bench.py's e2e leg and a non-torch host would call):
+ * the teacher-side filter step over a pool of n (A,Rgt) pairs living in HOST memory
+ * (pinned for full PCIe rate).  Chunks are copied H2D, run through K2 (+fused first
+ * histogram) and copied back D2H on alternating streams; then K3 selects the k-th
+ * smallest entropy of the whole pool and the mask is emitted and copied back.
+ * Host outputs nullable; threshold/kept written on return (the call blocks). */
+typedef struct suhpe_pipeline suhpe_pipeline;
+int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk);
+int suhpe_pipeline_destroy(suhpe_pipeline* p);
+int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
+                             float overreg, uint64_t k, float* nll_host, float* grad_host,
+                             float* entropy_host, uint8_t* mask_host, float* threshold, uint64_t* kept);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMIUHPE_B200_H */

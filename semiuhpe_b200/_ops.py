@@ -1,0 +1,223 @@
+"""Tensor-level wrappers over the C ABI (one CUDA launch each, on the current stream).
+
+These allocate the outputs with torch's caching allocator, pass raw device
+pointers through ``ctypes`` and translate the device status word into the
+exceptions the reference raises.  Nothing here computes: no torch math, no CPU.
+"""
+import ctypes
+
+import torch
+
+import semiuhpe_b200 as _pkg
+from . import _capi
+from ._capi import as_records, check, lib, ptr, stream
+
+_STATUS = {}
+
+
+def _status_word(device):
+    t = _STATUS.get(device)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _STATUS[device] = t
+    return t
+
+
+def _raise_from_status(status, what):
+    """One 4-byte read (sync), only when error checking is on (reference parity:
+    torch.svd raises LinAlgError on NaN/Inf, pytorch3d raises ValueError)."""
+    if not _pkg.error_checking():
+        return
+    bits = int(status.item())
+    if bits:
+        status.zero_()
+        if bits & _capi.STATUS_NONFINITE:
+            raise torch.linalg.LinAlgError(
+                f"{what}: the input contains non-finite values (torch.svd in the reference fails the same way)")
+        if bits & _capi.STATUS_TRACE_RANGE:
+            raise ValueError("A matrix has trace outside valid range [-1-eps,3+eps].")
+
+
+def fisher_fused(A, R=None, overreg=1.0, *, nll=False, grad=False, rot=False, entropy=False,
+                 logC=False, S=False, G=False, hist=None, what="fisher"):
+    """K2.  Returns a dict of the requested outputs (keys = argument names)."""
+    A9 = as_records(A, "A")
+    n = A9.shape[0]
+    R9 = None
+    if R is not None:
+        R9 = as_records(R, "R")
+        if R9.shape[0] != n:
+            raise RuntimeError(f"shape mismatch: A has {n} matrices, R has {R9.shape[0]}")
+    dev = A9.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = {}
+    if nll: out["nll"] = new(n)
+    if grad: out["grad"] = new(n, 9)
+    if rot: out["rot"] = new(n, 3, 3)
+    if entropy: out["entropy"] = new(n)
+    if logC: out["logC"] = new(n)
+    if S: out["S"] = new(n, 3)
+    if G: out["G"] = new(n, 3)
+    if n == 0:
+        return out
+    status = _status_word(dev)
+    with torch.cuda.device(dev):
+        check(lib().suhpe_fisher_fused_f32(
+            ptr(A9), ptr(R9), n, float(overreg), ptr(out.get("nll")), ptr(out.get("grad")),
+            ptr(out.get("rot")), ptr(out.get("entropy")), ptr(out.get("logC")), ptr(out.get("S")),
+            ptr(out.get("G")), ptr(hist), ptr(status), stream()), what)
+    _raise_from_status(status, what)
+    return out
+
+
+def fisher_from_s(S, *, logC=True, G=False, entropy=False):
+    """K2 on given singular values (logC_F)."""
+    S3 = as_records(S, "S", 3)
+    n = S3.shape[0]
+    dev = S3.device
+    out = {}
+    if logC: out["logC"] = torch.empty(n, dtype=torch.float32, device=dev)
+    if G: out["G"] = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    if entropy: out["entropy"] = torch.empty(n, dtype=torch.float32, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            check(lib().suhpe_fisher_from_s_f32(ptr(S3), n, ptr(out.get("logC")), ptr(out.get("G")),
+                                                ptr(out.get("entropy")), None, stream()), "logC_F")
+    return out
+
+
+def proper_svd(A, *, rot=True, S=False, U=False, V=False, what="svd"):
+    """K1."""
+    A9 = as_records(A, "A")
+    n = A9.shape[0]
+    dev = A9.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = {}
+    if rot: out["rot"] = new(n, 3, 3)
+    if S: out["S"] = new(n, 3)
+    if U: out["U"] = new(n, 3, 3)
+    if V: out["V"] = new(n, 3, 3)
+    if n == 0:
+        return out
+    status = _status_word(dev)
+    with torch.cuda.device(dev):
+        check(lib().suhpe_proper_svd_f32(ptr(A9), n, ptr(out.get("rot")), ptr(out.get("S")),
+                                         ptr(out.get("U")), ptr(out.get("V")), ptr(status), stream()), what)
+    _raise_from_status(status, what)
+    return out
+
+
+def laplace_nll(A, R, grids, *, grad=False, mode=True, logF=False):
+    """K2L."""
+    A9 = as_records(A, "pred")
+    R9 = as_records(R, "gt")
+    g9 = as_records(grids, "grids")
+    n, N = A9.shape[0], g9.shape[0]
+    if R9.shape[0] != n:
+        raise RuntimeError(f"shape mismatch: pred has {n} matrices, gt has {R9.shape[0]}")
+    dev = A9.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = {"nll": new(n)}
+    if grad: out["grad"] = new(n, 9)
+    if mode: out["mode"] = new(n, 3, 3)
+    if logF: out["logF"] = new(n)
+    if n == 0:
+        return out
+    status = _status_word(dev)
+    with torch.cuda.device(dev):
+        check(lib().suhpe_laplace_nll_f32(ptr(A9), ptr(R9), n, ptr(g9), N, ptr(out["nll"]), ptr(out.get("grad")),
+                                          ptr(out.get("mode")), ptr(out.get("logF")), ptr(status), stream()),
+              "laplace_nll")
+    _raise_from_status(status, "laplace_nll")
+    return out
+
+
+def so3_metrics(Rp, Rg=None, gt_euler=None, *, full_range=False, geo=False, frob=False, euler=False,
+                abs_err=False, mae=False, sums=False):
+    """K4."""
+    P9 = as_records(Rp, "pred")
+    n = P9.shape[0]
+    G9 = as_records(Rg, "gt") if Rg is not None else None
+    E3 = as_records(gt_euler, "gt_euler", 3) if gt_euler is not None else None
+    for name, t in (("gt", G9), ("gt_euler", E3)):
+        if t is not None and t.shape[0] != n:
+            raise RuntimeError(f"shape mismatch: pred has {n} rows, {name} has {t.shape[0]}")
+    dev = P9.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = {}
+    if geo: out["geo"] = new(n)
+    if frob: out["frob"] = new(n)
+    if euler: out["euler"] = new(n, 3)
+    if abs_err: out["abs_err"] = new(n, 3)
+    if mae: out["mae"] = new(n)
+    if sums: out["sums"] = torch.zeros(8, dtype=torch.float64, device=dev)
+    if n == 0:
+        return out
+    status = _status_word(dev)
+    with torch.cuda.device(dev):
+        check(lib().suhpe_so3_metrics_f32(ptr(P9), ptr(G9), ptr(E3), n, int(bool(full_range)),
+                                          ptr(out.get("geo")), ptr(out.get("frob")), ptr(out.get("euler")),
+                                          ptr(out.get("abs_err")), ptr(out.get("mae")), ptr(out.get("sums")),
+                                          ptr(status), stream()), "so3_metrics")
+    if geo or sums:
+        _raise_from_status(status, "so3_relative_angle")
+    return out
+
+
+class SelectWorkspace:
+    """Device scratch of the radix select: 32-byte state + two 2048-bin uint64 histograms."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.state = torch.zeros(_capi.SELECT_STATE_BYTES // 8, dtype=torch.int64, device=self.device)
+        self.hist = torch.zeros((2, _capi.HIST_BINS), dtype=torch.int64, device=self.device)
+
+    def threshold_ptr(self):
+        return ctypes.c_void_p(lib().suhpe_select_threshold_ptr(ptr(self.state)))
+
+    def read(self):
+        thr, key, kept = ctypes.c_float(), ctypes.c_uint32(), ctypes.c_uint64()
+        with torch.cuda.device(self.device):
+            check(lib().suhpe_select_read(ptr(self.state), ctypes.byref(thr), ctypes.byref(key),
+                                          ctypes.byref(kept), stream()), "select_read")
+        return thr.value, key.value, kept.value
+
+
+def _entropy_vector(e):
+    if not e.is_cuda:
+        raise RuntimeError("entropy must be a CUDA tensor: semiuhpe_b200 has no CPU path")
+    if e.dtype != torch.float32:
+        raise TypeError("entropy must be float32")
+    e = e.detach().reshape(-1)
+    return e if e.is_contiguous() else e.contiguous()
+
+
+def entropy_threshold_device(entropy, k, ws=None, first_pass_hist=None):
+    """K3 on one GPU: leaves the k-th smallest entropy in ``ws.state`` (no host sync)."""
+    e = _entropy_vector(entropy)
+    n = e.numel()
+    if not 0 <= k < n:
+        raise IndexError(f"index {k} is out of bounds for axis 0 with size {n}")
+    ws = ws or SelectWorkspace(e.device)
+    with torch.cuda.device(e.device):
+        check(lib().suhpe_entropy_threshold_f32(ptr(e), n, k, ptr(ws.state), ptr(ws.hist[1]),
+                                                ptr(first_pass_hist), stream()), "entropy_threshold")
+    return ws
+
+
+def entropy_mask(entropy, thr, ws=None, want_mask=True):
+    """mask = entropy < thr (strict).  ``thr``: python float or a SelectWorkspace
+    (threshold read on the device).  Returns (mask bool tensor | None, kept-count tensor int64[1])."""
+    e = _entropy_vector(entropy)
+    n = e.numel()
+    mask = torch.empty(n, dtype=torch.bool, device=e.device) if want_mask else None
+    kept = torch.zeros(1, dtype=torch.int64, device=e.device)
+    if n:
+        with torch.cuda.device(e.device):
+            if isinstance(thr, SelectWorkspace):
+                check(lib().suhpe_entropy_mask_f32(ptr(e), n, thr.threshold_ptr(), 0.0, ptr(mask), ptr(kept),
+                                                   stream()), "entropy_mask")
+            else:
+                check(lib().suhpe_entropy_mask_f32(ptr(e), n, None, float(thr), ptr(mask), ptr(kept),
+                                                   stream()), "entropy_mask")
+    return mask, kept

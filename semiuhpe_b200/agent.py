@@ -1,0 +1,124 @@
+"""Drop-ins for the filter / threshold / metric slice of the reference's ``SSLAgent``
+(src/agent.py:148-150, 229-232, 357-417, 420-455).
+
+The reference's agent class itself (networks, optimiser, EMA, checkpoints) is out
+of scope and keeps running unchanged; it only needs these functions swapped in
+(INTEGRATION.md).  Everything below runs on the GPU: the pool threshold is an
+exact radix select over the entropies where they were produced (K3) instead of a
+device->host copy per batch plus ``numpy.sort``.
+"""
+import torch
+
+from . import _ops
+from .fisher.fisher_utils import fisher_entropy
+
+
+# ------------------------------------------------------------------ a12: filter
+def pool_index(n, left_ratio):
+    """``index = int(len(entropy_all) * left_ratio)`` (src/agent.py:406): Python float
+    product, truncation toward zero.  ``left_ratio >= 1`` raises IndexError like the
+    reference's numpy indexing at :407 (negative ratios wrap there; rejected here)."""
+    index = int(n * left_ratio)
+    if not 0 <= index < n:
+        raise IndexError(f"index {index} is out of bounds for axis 0 with size {n}")
+    return index
+
+
+def entropy_threshold(entropies, left_ratio, workspace=None, first_pass_hist=None, sync=True):
+    """k-th smallest entropy of the pool, k = int(n*left_ratio), in ``numpy.sort`` order
+    (ascending, NaN last) -- the value ``entropy_all.sort(); entropy_all[index]`` of
+    src/agent.py:403-407.  Returns a Python float, or with ``sync=False`` the
+    :class:`semiuhpe_b200._ops.SelectWorkspace` holding it on the device."""
+    e = entropies.reshape(-1)
+    k = pool_index(e.numel(), left_ratio)
+    ws = _ops.entropy_threshold_device(e, k, workspace, first_pass_hist)
+    if not sync:
+        return ws
+    return ws.read()[0]
+
+
+def entropy_mask(entropy, conf_thres):
+    """``mask = entropy < conf_thres`` and ``mask_ratio = mask.sum() / len(mask)``
+    (src/agent.py:148-150).  ``conf_thres``: float (yml value or a threshold returned by
+    :func:`entropy_threshold`) or a SelectWorkspace (threshold stays on the device)."""
+    mask, kept = _ops.entropy_mask(entropy, conf_thres)
+    ratio = kept.to(torch.float32) / max(mask.numel(), 1)
+    return mask, ratio.reshape(())
+
+
+def dynamic_entropy_filter(pred_weak, left_ratio, return_threshold=True):
+    """Teacher-batch filter of BASELINE config 2: entropies of the unlabeled teacher
+    outputs (K2), threshold at rank int(n*left_ratio) (K3), strict-< keep mask -- three
+    launches chained on the current stream, no host sync unless the threshold value is
+    requested.  Returns (entropy, mask, mask_ratio[, threshold float])."""
+    A = pred_weak.reshape(-1, 9)
+    n = A.shape[0]
+    k = pool_index(n, left_ratio)
+    ws = _ops.SelectWorkspace(A.device)
+    ws.hist.zero_()
+    ent = _ops.fisher_fused(A, None, 1.0, entropy=True, hist=ws.hist[0], what="fisher_entropy")["entropy"]
+    _ops.entropy_threshold_device(ent, k, ws, first_pass_hist=ws.hist[0])
+    mask, kept = _ops.entropy_mask(ent, ws)
+    ratio = (kept.to(torch.float32) / n).reshape(())
+    if return_threshold:
+        return ent, mask, ratio, ws.read()[0]
+    return ent, mask, ratio
+
+
+def compute_dynamic_entropy_threshold(agent, ulb_train_bar):
+    """Function form of ``SSLAgent.compute_dynamic_entropy_threshold`` (src/agent.py:357-417):
+    run the EMA teacher over the unlabeled loader, collect ``fisher_entropy`` of every
+    batch ON THE DEVICE, select the ``left_ratio`` percentile and store it in
+    ``agent.config.conf_thres``.  (The reference's optional feature dump, ``save_feat``,
+    is host-side bookkeeping and stays with the reference agent.)"""
+    agent.ema_net.eval()
+    chunks = []
+    with torch.no_grad():
+        for ulb_data in ulb_train_bar:
+            pred_weak = agent.ema_net(ulb_data.get("img").cuda())
+            chunks.append(fisher_entropy(pred_weak))
+    entropy_all = torch.cat(chunks, 0)
+    thr = entropy_threshold(entropy_all, agent.config.left_ratio)
+    print("The best dynamic entropy threshold is:", thr)
+    agent.config.conf_thres = thr
+    return thr
+
+
+# ------------------------------------------------------------ a13..a16: metrics
+def compute_err_deg_from_matrices(pred, gt, gt_euler=None):
+    """(b,3,3),(b,3,3)[,(b,3) degrees] -> (b,) error in degrees (src/agent.py:447-455):
+    geodesic angle via pytorch3d's ``so3_relative_angle`` semantics when ``gt_euler`` is
+    None, else the mean absolute (pitch,yaw,roll) error."""
+    if gt_euler is None:
+        return _ops.so3_metrics(pred, gt, geo=True)["geo"]
+    return _ops.so3_metrics(pred, gt, gt_euler, full_range=False, mae=True)["mae"]
+
+
+def compute_err_deg_from_quats(pred, gt):
+    """src/agent.py:420-424: geodesic error of two real-first quaternion batches."""
+    return compute_err_deg_from_matrices(_quat_to_matrix(pred), _quat_to_matrix(gt))
+
+
+def _quat_to_matrix(q):
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(q.shape[:-1] + (3, 3))
+
+
+def eval_rotation_metrics(pred, gt, gt_euler=None):
+    """One K4 launch for the evaluation loop of eval.py:76-98,125-133.
+
+    With ``gt_euler`` (degrees): per-angle absolute errors (n,3) and their means
+    ``(pitch, yaw, roll, mean)``; without: geodesic degrees (n,), Frobenius distance
+    (n,) and their means.  Means are accumulated in fp64 on the device."""
+    n = pred.reshape(-1, 9).shape[0]
+    if gt_euler is not None:
+        out = _ops.so3_metrics(pred, gt, gt_euler, full_range=False, abs_err=True, mae=True, sums=True)
+        s = out["sums"] / max(n, 1)
+        return dict(abs_err=out["abs_err"], mae=out["mae"], pitch=s[2], yaw=s[3], roll=s[4], mean=s[5])
+    out = _ops.so3_metrics(pred, gt, geo=True, frob=True, sums=True)
+    s = out["sums"] / max(n, 1)
+    return dict(geodesic_deg=out["geo"], frobenius=out["frob"], geodesic_mean=s[0], frobenius_mean=s[1])

@@ -1,0 +1,306 @@
+// capi.cu -- the extern "C" boundary declared in include/semiuhpe_b200.h.
+// No torch types, no exceptions, no hidden synchronisation (except the _host
+// pipeline and suhpe_select_read, which return host values).
+#include "../../include/semiuhpe_b200.h"
+#include "kernels.cuh"
+
+#include <new>
+#include <stdio.h>
+#include <string.h>
+
+using namespace suhpe;
+
+namespace {
+
+static_assert(sizeof(SelectState) == SUHPE_SELECT_STATE_BYTES, "SelectState layout is part of the ABI");
+static_assert(kHistBinsMax == SUHPE_HIST_BINS, "histogram width is part of the ABI");
+static_assert(kStatusNonFinite == SUHPE_STATUS_NONFINITE && kStatusTraceRange == SUHPE_STATUS_TRACE_RANGE, "status bits");
+
+inline int rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
+inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- FP32 pipe probe ---------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters) {
+    const float seed = 1.0f + 1e-7f * (float)(threadIdx.x + blockIdx.x);
+    if (VARIANT == 1) {
+        // 8 independent packed chains: x = x * a + b on (lo,hi) pairs
+        unsigned long long x[8], a, b;
+        const float af = 0.9999f, bf = 1e-4f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(af));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const float v = seed + (float)c; asm("mov.b64 %0, {%1, %1};" : "=l"(x[c]) : "f"(v)); }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[c]) : "l"(a), "l"(b));
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[c])); acc += lo + hi; }
+        if (acc == 123.456f) sink[0] = acc;
+    } else {
+        float x[8];
+        const float a = 0.9999f, b = 1e-4f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = seed + (float)c;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = fmaf(x[c], a, b);
+                if (VARIANT == 2) {
+                    // one MUFU.EX2 per 8 FMA, on its own dependency chain slot
+                    float y;
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x[r & 7]));
+                    x[(r + 1) & 7] += y * 1e-30f;
+                }
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc += x[c];
+        if (acc == 123.456f) sink[0] = acc;
+    }
+}
+
+}  // namespace
+
+namespace suhpe {
+cudaError_t launch_fp32_probe(float* sink, int variant, int iters, int blocks, cudaStream_t stream) {
+    if (variant == 0) fp32_probe_kernel<0><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 1) fp32_probe_kernel<1><<<blocks, 256, 0, stream>>>(sink, iters);
+    else fp32_probe_kernel<2><<<blocks, 256, 0, stream>>>(sink, iters);
+    return cudaGetLastError();
+}
+}  // namespace suhpe
+
+// ---- host-buffer pipeline ------------------------------------------------------
+struct suhpe_pipeline {
+    long long max_n, chunk;
+    cudaStream_t streams[2];
+    cudaEvent_t done[2];
+    float *dA[2], *dR[2], *dGrad[2], *dNll[2];
+    float* dEnt;             // (max_n) entropies of the whole pool stay resident for the select
+    uint8_t* dMask;          // (max_n)
+    unsigned long long* dHist;   // 2 x SUHPE_HIST_BINS: [0] fused first pass, [1] scratch
+    SelectState* dState;
+    int* dStatus;
+    SelectState* hState;     // pinned
+    int* hStatus;            // pinned
+};
+
+extern "C" {
+
+int suhpe_abi_version(void) { return SUHPE_ABI_VERSION; }
+
+const char* suhpe_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == SUHPE_EINVAL) return "invalid argument";
+    if (code < 0) return cudaGetErrorString((cudaError_t)(-code));
+    return "unknown";
+}
+
+int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U, float* V,
+                         int* status, void* stream) {
+    if (n < 0 || (n > 0 && !A)) return SUHPE_EINVAL;
+    SvdArgs p{A, (long long)n, R, S, U, V, status, false};
+    return rc(launch_proper_svd(p, st(stream)));
+}
+
+int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg,
+                           float* nll, float* grad, float* Rout, float* entropy, float* logC,
+                           float* S, float* G, uint64_t* hist, int* status, void* stream) {
+    if (n < 0 || (n > 0 && !A)) return SUHPE_EINVAL;
+    FisherArgs p{};
+    p.A = A; p.Rgt = Rgt; p.n = (long long)n; p.overreg = overreg;
+    p.nll = nll; p.grad = grad; p.Rout = Rout; p.entropy = entropy; p.logC = logC; p.S = S; p.G = G;
+    p.hist = reinterpret_cast<unsigned long long*>(hist); p.status = status;
+    return rc(launch_fisher_fused(p, st(stream)));
+}
+
+int suhpe_fisher_from_s_f32(const float* S, int64_t n, float* logC, float* G, float* entropy,
+                            int* status, void* stream) {
+    if (n < 0 || (n > 0 && !S)) return SUHPE_EINVAL;
+    FisherArgs p{};
+    p.Sin = S; p.n = (long long)n; p.overreg = 1.0f;
+    p.logC = logC; p.G = G; p.entropy = entropy; p.status = status;
+    return rc(launch_fisher_fused(p, st(stream)));
+}
+
+int suhpe_laplace_nll_f32(const float* A, const float* Rgt, int64_t n, const float* grid, int32_t N,
+                          float* nll, float* grad, float* mode, float* logF, int* status, void* stream) {
+    if (n < 0 || N <= 0 || (n > 0 && (!A || !Rgt || !grid || !nll))) return SUHPE_EINVAL;
+    LaplaceArgs p{A, Rgt, (long long)n, grid, (int)N, nll, grad, mode, logF, status};
+    return rc(launch_laplace(p, st(stream)));
+}
+
+int suhpe_select_init(void* state, uint64_t k, void* stream) {
+    if (!state) return SUHPE_EINVAL;
+    return rc(launch_select_init(static_cast<SelectState*>(state), k, st(stream)));
+}
+
+int suhpe_select_hist_f32(const float* entropy, int64_t n, int32_t pass, const void* state,
+                          uint64_t* hist, void* stream) {
+    if (n < 0 || pass < 1 || pass > 3 || !state || !hist || (n > 0 && !entropy)) return SUHPE_EINVAL;
+    return rc(launch_select_hist(entropy, (long long)n, pass, static_cast<const SelectState*>(state),
+                                 reinterpret_cast<unsigned long long*>(hist), st(stream)));
+}
+
+int suhpe_select_scan(const uint64_t* hist_parts, int32_t parts, int32_t pass, void* state, void* stream) {
+    if (!hist_parts || parts < 1 || pass < 1 || pass > 3 || !state) return SUHPE_EINVAL;
+    return rc(launch_select_scan(reinterpret_cast<const unsigned long long*>(hist_parts), parts, pass,
+                                 static_cast<SelectState*>(state), st(stream)));
+}
+
+int suhpe_entropy_threshold_f32(const float* entropy, int64_t n, uint64_t k, void* state,
+                                uint64_t* hist_scratch, const uint64_t* first_pass_hist, void* stream) {
+    if (n <= 0 || !entropy || !state || !hist_scratch || k >= (uint64_t)n) return SUHPE_EINVAL;
+    SelectState* s = static_cast<SelectState*>(state);
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(hist_scratch);
+    cudaError_t e = launch_select_init(s, k, st(stream));
+    for (int pass = 1; pass <= 3 && e == cudaSuccess; ++pass) {
+        if (pass == 1 && first_pass_hist) {
+            e = launch_select_scan(reinterpret_cast<const unsigned long long*>(first_pass_hist), 1, 1, s, st(stream));
+            continue;
+        }
+        e = launch_select_hist(entropy, (long long)n, pass, s, h, st(stream));
+        if (e == cudaSuccess) e = launch_select_scan(h, 1, pass, s, st(stream));
+    }
+    return rc(e);
+}
+
+const float* suhpe_select_threshold_ptr(const void* state) {
+    return state ? &static_cast<const SelectState*>(state)->threshold : nullptr;
+}
+
+int suhpe_select_read(const void* state, float* threshold, uint32_t* key, uint64_t* kept, void* stream) {
+    if (!state) return SUHPE_EINVAL;
+    SelectState h;
+    cudaError_t e = cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st(stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st(stream));
+    if (e != cudaSuccess) return rc(e);
+    if (threshold) *threshold = h.threshold;
+    if (key) *key = h.threshold_key;
+    if (kept) *kept = h.kept;
+    return 0;
+}
+
+int suhpe_entropy_mask_f32(const float* entropy, int64_t n, const float* thr_dev, float thr_host,
+                           uint8_t* mask, uint64_t* kept, void* stream) {
+    if (n < 0 || (n > 0 && !entropy)) return SUHPE_EINVAL;
+    return rc(launch_mask(entropy, (long long)n, thr_dev, thr_host, mask,
+                          reinterpret_cast<unsigned long long*>(kept), st(stream)));
+}
+
+int suhpe_so3_metrics_f32(const float* Rp, const float* Rg, const float* gt_euler_deg, int64_t n,
+                          int32_t full_range, float* geo_deg, float* frob, float* euler,
+                          float* abs_err, float* mae, double* sums, int* status, void* stream) {
+    if (n < 0 || (n > 0 && !Rp)) return SUHPE_EINVAL;
+    if (!Rg && (geo_deg || frob)) return SUHPE_EINVAL;
+    if (!gt_euler_deg && (abs_err || mae)) return SUHPE_EINVAL;
+    MetricsArgs p{Rp, Rg, gt_euler_deg, (long long)n, (int)full_range, geo_deg, frob, euler, abs_err, mae, sums, status};
+    return rc(launch_metrics(p, st(stream)));
+}
+
+int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks, void* stream) {
+    if (!sink || iters < 1 || blocks < 1 || variant < 0 || variant > 2) return SUHPE_EINVAL;
+    return rc(launch_fp32_probe(sink, variant, iters, blocks, st(stream)));
+}
+
+// ---- pipeline ---------------------------------------------------------------------
+int suhpe_pipeline_destroy(suhpe_pipeline* p) {
+    if (!p) return 0;
+    for (int i = 0; i < 2; ++i) {
+        if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+        if (p->done[i]) cudaEventDestroy(p->done[i]);
+        cudaFree(p->dA[i]); cudaFree(p->dR[i]); cudaFree(p->dGrad[i]); cudaFree(p->dNll[i]);
+    }
+    cudaFree(p->dEnt); cudaFree(p->dMask); cudaFree(p->dHist); cudaFree(p->dState); cudaFree(p->dStatus);
+    if (p->hState) cudaFreeHost(p->hState);
+    if (p->hStatus) cudaFreeHost(p->hStatus);
+    delete p;
+    return 0;
+}
+
+int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk) {
+    if (!out || max_n <= 0 || chunk <= 0) return SUHPE_EINVAL;
+    suhpe_pipeline* p = new (std::nothrow) suhpe_pipeline();
+    if (!p) return SUHPE_EINVAL;
+    memset(p, 0, sizeof(*p));
+    if (chunk > max_n) chunk = max_n;
+    chunk = (chunk + 31) & ~31LL;                 // keep every chunk base 16-byte aligned (32 records = 1152 B)
+    p->max_n = max_n; p->chunk = chunk;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(q, bytes); };
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming);
+        A((void**)&p->dA[i], (size_t)chunk * 36); A((void**)&p->dR[i], (size_t)chunk * 36);
+        A((void**)&p->dGrad[i], (size_t)chunk * 36); A((void**)&p->dNll[i], (size_t)chunk * 4);
+    }
+    A((void**)&p->dEnt, (size_t)max_n * 4); A((void**)&p->dMask, (size_t)max_n);
+    A((void**)&p->dHist, sizeof(unsigned long long) * 2 * SUHPE_HIST_BINS);
+    A((void**)&p->dState, sizeof(SelectState)); A((void**)&p->dStatus, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->hState, sizeof(SelectState));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->hStatus, sizeof(int));
+    if (e != cudaSuccess) { suhpe_pipeline_destroy(p); return rc(e); }
+    *out = p;
+    return 0;
+}
+
+int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
+                             float overreg, uint64_t k, float* nll_host, float* grad_host,
+                             float* entropy_host, uint8_t* mask_host, float* threshold, uint64_t* kept) {
+    if (!p || !A_host || n <= 0 || n > p->max_n || k >= (uint64_t)n) return SUHPE_EINVAL;
+    cudaError_t e = cudaSuccess;
+#define CK(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    cudaStream_t s0 = p->streams[0], s1 = p->streams[1];
+    CK(cudaMemsetAsync(p->dHist, 0, sizeof(unsigned long long) * 2 * SUHPE_HIST_BINS, s0));
+    CK(cudaMemsetAsync(p->dStatus, 0, sizeof(int), s0));
+    CK(cudaEventRecord(p->done[0], s0));
+    CK(cudaStreamWaitEvent(s1, p->done[0], 0));
+    long long nchunks = (n + p->chunk - 1) / p->chunk;
+    for (long long c = 0; c < nchunks && e == cudaSuccess; ++c) {
+        const int b = (int)(c & 1);
+        cudaStream_t s = p->streams[b];
+        const long long base = c * p->chunk;
+        const long long cnt = (n - base < p->chunk) ? (n - base) : p->chunk;
+        CK(cudaMemcpyAsync(p->dA[b], A_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, s));
+        if (Rgt_host) CK(cudaMemcpyAsync(p->dR[b], Rgt_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, s));
+        FisherArgs a{};
+        a.A = p->dA[b]; a.Rgt = Rgt_host ? p->dR[b] : nullptr; a.n = cnt; a.overreg = overreg;
+        a.nll = nll_host ? p->dNll[b] : nullptr;
+        a.grad = grad_host ? p->dGrad[b] : nullptr;
+        a.entropy = p->dEnt + base;
+        a.hist = p->dHist; a.status = p->dStatus;
+        CK(launch_fisher_fused(a, s));
+        if (nll_host) CK(cudaMemcpyAsync(nll_host + base, p->dNll[b], (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        if (grad_host) CK(cudaMemcpyAsync(grad_host + base * 9, p->dGrad[b], (size_t)cnt * 36, cudaMemcpyDeviceToHost, s));
+        if (entropy_host) CK(cudaMemcpyAsync(entropy_host + base, p->dEnt + base, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+    }
+    // join stream 1 into stream 0, then select + mask on the resident entropies
+    CK(cudaEventRecord(p->done[1], s1));
+    CK(cudaStreamWaitEvent(s0, p->done[1], 0));
+    if (e == cudaSuccess) {
+        int r = suhpe_entropy_threshold_f32(p->dEnt, n, k, p->dState,
+                                            reinterpret_cast<uint64_t*>(p->dHist + SUHPE_HIST_BINS),
+                                            reinterpret_cast<const uint64_t*>(p->dHist), s0);
+        if (r != 0) return r;
+    }
+    CK(launch_mask(p->dEnt, n, &p->dState->threshold, 0.f, mask_host ? p->dMask : nullptr, &p->dState->kept, s0));
+    if (mask_host) CK(cudaMemcpyAsync(mask_host, p->dMask, (size_t)n, cudaMemcpyDeviceToHost, s0));
+    CK(cudaMemcpyAsync(p->hState, p->dState, sizeof(SelectState), cudaMemcpyDeviceToHost, s0));
+    CK(cudaMemcpyAsync(p->hStatus, p->dStatus, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+#undef CK
+    if (e != cudaSuccess) return rc(e);
+    if (threshold) *threshold = p->hState->threshold;
+    if (kept) *kept = p->hState->kept;
+    return (*p->hStatus & SUHPE_STATUS_NONFINITE) ? 1 : 0;   // >0: completed, non-finite input seen
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// kernels.cuh -- argument blocks and launchers shared by the .cu files and capi.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace suhpe {
+
+// status bits written (atomicOr) by the kernels into an optional device word
+constexpr int kStatusNonFinite  = 1;   // A held NaN/Inf (reference: torch.svd raises)
+constexpr int kStatusTraceRange = 2;   // trace(R1 R2^T) outside [-1-1e-4, 3+1e-4] (pytorch3d raises ValueError)
+
+// radix-select digit layout over the 32-bit monotone entropy key: 11 | 11 | 10 bits
+constexpr int kHistBins1 = 2048, kHistShift1 = 21;
+constexpr int kHistBins2 = 2048, kHistShift2 = 10;
+constexpr int kHistBins3 = 1024, kHistShift3 = 0;
+constexpr int kHistBinsMax = 2048;
+
+struct FisherArgs {
+    const float* A;        // (n,9) network output, row-major 3x3 records
+    const float* Rgt;      // (n,9) target rotations or nullptr (entropy / projection only)
+    const float* Sin;      // (n,3) singular values given directly (then A, Rgt, grad, Rout unused) | nullptr
+    long long n;
+    float overreg;
+    float* nll;            // (n)   -<A,R> + overreg*logC          | nullptr
+    float* grad;           // (n,9) d nll_i / d A_i                | nullptr
+    float* Rout;           // (n,9) proper-SVD rotation            | nullptr
+    float* entropy;        // (n)                                  | nullptr
+    float* logC;           // (n)   log normaliser                 | nullptr
+    float* S;              // (n,3) proper singular values         | nullptr
+    float* G;              // (n,3) d logC / d S                   | nullptr
+    unsigned long long* hist;  // (2048) += histogram of the top 11 key bits of entropy | nullptr
+    int* status;           // |= kStatus* | nullptr
+    int samples_per_warp;  // set by the launcher
+    bool vec_ok;           // set by the launcher: float4 tile I/O allowed
+};
+
+struct SvdArgs {
+    const float* A; long long n;
+    float* R; float* S; float* U; float* V;   // each nullable
+    int* status;
+    bool vec_ok;
+};
+
+struct LaplaceArgs {
+    const float* A;        // (n,9)
+    const float* Rgt;      // (n,9)
+    long long n;
+    const float* grid;     // (N,9) SO(3) grid, device resident
+    int N;
+    float* nll;            // (n)
+    float* grad;           // (n,9) | nullptr
+    float* mode;           // (n,9) | nullptr
+    float* logF;           // (n)   | nullptr
+    int* status;
+};
+
+struct MetricsArgs {
+    const float* Rp;       // (n,9) predictions
+    const float* Rg;       // (n,9) ground truth | nullptr (Euler of Rp only)
+    const float* gt_euler; // (n,3) degrees (pitch,yaw,roll) | nullptr
+    long long n;
+    int full_range;
+    float* geo_deg;        // (n)   | nullptr
+    float* frob;           // (n)   | nullptr
+    float* euler;          // (n,3) radians | nullptr
+    float* abs_err;        // (n,3) |euler_deg - gt| | nullptr
+    float* mae;            // (n)   mean_3 abs_err | nullptr
+    double* sums;          // (8) += [geo, frob, |dp|, |dy|, |dr|, mae, 0, 0] | nullptr
+    int* status;
+};
+
+cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream);
+cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream);
+cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream);
+cudaError_t launch_metrics(MetricsArgs p, cudaStream_t stream);
+
+// ---- radix select over entropy keys -----------------------------------------
+// state block kept on the device between passes (no host round trip on 1 GPU)
+struct SelectState {
+    unsigned long long k_remaining;   // rank still to locate inside the current prefix
+    unsigned int prefix;              // key bits fixed so far (high bits)
+    unsigned int pass;                // passes completed
+    unsigned int threshold_key;       // valid after pass 3
+    float threshold;                  // valid after pass 3
+    unsigned long long kept;          // # entropies strictly below threshold (after mask)
+};
+
+cudaError_t launch_select_hist(const float* e, long long n, int pass, const SelectState* state,
+                               unsigned long long* hist, cudaStream_t stream);
+// hist_parts: (parts, bins) gathered histograms, summed on the fly
+cudaError_t launch_select_scan(const unsigned long long* hist_parts, int parts, int pass,
+                               SelectState* state, cudaStream_t stream);
+cudaError_t launch_select_init(SelectState* state, unsigned long long k, cudaStream_t stream);
+cudaError_t launch_mask(const float* e, long long n, const float* thr_dev, float thr_host,
+                        uint8_t* mask, unsigned long long* kept, cudaStream_t stream);
+
+// FP32 pipe probe (roofline denominator measured on the box): returns FMA count executed
+cudaError_t launch_fp32_probe(float* sink, int variant, int iters, int blocks, cudaStream_t stream);
+
+}  // namespace suhpe

@@ -1,0 +1,432 @@
+// so3_math.cuh -- per-sample SO(3) arithmetic shared by all kernels (sm_100a).
+//
+// Everything here is scalar, register-resident and branch-light; the kernels in
+// fisher_kernels.cu / laplace_kernels.cu / metrics_kernels.cu decide how samples
+// and quadrature nodes are spread over lanes.  The functions are
+// __host__ __device__ so that tests/emul (a host-only build used by the CPU test
+// suite) can exercise exactly this source without a GPU; the product never runs
+// the host instantiation.
+//
+// Reference behaviour restated (hnuzhy/SemiUHPE, paths relative to its root):
+//   proper SVD / rotation      src/fisher/fisher_utils.py:27-31,39-48
+//                              src/fisher/between_bingham_fisher.py:63-82
+//   A&S Bessel polynomials     src/fisher/torch_norm_factor.py:4-19
+//   512-node trapezoid         src/fisher/torch_norm_factor.py:21-31
+//   integrands                 src/fisher/torch_norm_factor.py:33-63
+//   Euler angles               src/utils.py:232-260
+//   geodesic angle             pytorch3d 0.7.2 so3_relative_angle (src/agent.py:450)
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define SUHPE_HD __host__ __device__ __forceinline__
+
+namespace suhpe {
+
+// ----------------------------------------------------------------------------
+// MUFU wrappers.  On the device these are single SFU instructions; the host
+// versions exist only for tests/emul.
+// ----------------------------------------------------------------------------
+SUHPE_HD float mufu_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+SUHPE_HD float mufu_ex2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+SUHPE_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+SUHPE_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+SUHPE_HD float div_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+SUHPE_HD float sqrt_rn(float a) {
+#if defined(__CUDA_ARCH__)
+    return __fsqrt_rn(a);
+#else
+    return sqrtf(a);
+#endif
+}
+
+// ----------------------------------------------------------------------------
+// Proper SVD of a 3x3 matrix:  A = U diag(s) V^T,  det U = det V = +1,
+// s0 >= s1 >= |s2|, s2 carries the sign of det A.   R = U V^T is the rotation
+// the reference builds as [u1,u2,u3*det(U V^T)] V^T, and (s0,s1,s2) is its
+// S_sign.
+//
+// Method: one-sided (Hestenes) Jacobi on the columns of A -- rotations only, so
+// V stays in SO(3) -- followed by a rotation-only sort and a cross product for
+// the third left vector.  No division by the smallest singular value anywhere,
+// so rank-deficient input (A = 0 gives U = V = R = I like LAPACK) is safe.
+// ----------------------------------------------------------------------------
+constexpr int kJacobiSweeps = 5;
+
+SUHPE_HD void jacobi_pair(float* bp, float* bq, float* vp, float* vq) {
+    const float alpha = fmaf(bp[0], bp[0], fmaf(bp[1], bp[1], bp[2] * bp[2]));
+    const float beta  = fmaf(bq[0], bq[0], fmaf(bq[1], bq[1], bq[2] * bq[2]));
+    const float gamma = fmaf(bp[0], bq[0], fmaf(bp[1], bq[1], bp[2] * bq[2]));
+    const float d  = beta - alpha;
+    const float g2 = gamma + gamma;
+    const float h  = sqrt_rn(fmaf(d, d, g2 * g2));
+    const float den = fabsf(d) + h;
+    // tan(theta) = sgn(d) 2 gamma / (|d| + sqrt(d^2 + 4 gamma^2)); 0 when already orthogonal
+    float t = (den > 0.0f) ? div_rn((d < 0.0f) ? -g2 : g2, den) : 0.0f;
+    // rotations below the rounding level of the columns are skipped (also avoids
+    // denormal-driven drift when gamma ~ 0)
+    if (gamma * gamma <= 1e-16f * alpha * beta) t = 0.0f;
+    const float c = div_rn(1.0f, sqrt_rn(fmaf(t, t, 1.0f)));
+    const float s = t * c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float x = bp[i], y = bq[i];
+        bp[i] = fmaf(c, x, -s * y);
+        bq[i] = fmaf(s, x, c * y);
+        const float vx = vp[i], vy = vq[i];
+        vp[i] = fmaf(c, vx, -s * vy);
+        vq[i] = fmaf(s, vx, c * vy);
+    }
+}
+
+// swap columns p,q as the rotation (bp,bq) <- (bq,-bp): keeps det V = +1
+SUHPE_HD void rot_swap(bool doit, float* bp, float* bq, float* vp, float* vq, float& np_, float& nq_) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float x = bp[i], y = bq[i];
+        bp[i] = doit ? y : x;
+        bq[i] = doit ? -x : y;
+        const float vx = vp[i], vy = vq[i];
+        vp[i] = doit ? vy : vx;
+        vq[i] = doit ? -vx : vy;
+    }
+    const float a = np_, b = nq_;
+    np_ = doit ? b : a;
+    nq_ = doit ? a : b;
+}
+
+// A, U, V row-major 3x3.  Returns false when A holds a non-finite value
+// (the reference's torch.svd raises in that case).
+SUHPE_HD bool proper_svd3(const float* A, float* U, float* V, float* s) {
+    float amax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) amax = fmaxf(amax, fabsf(A[i]));
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) finite = finite && (fabsf(A[i]) <= 3.402823466e38f);
+    // exact power-of-two prescale: columns land in [1,2) * O(1); undone exactly on s
+#if defined(__CUDA_ARCH__)
+    const int ebits = (__float_as_int(amax) >> 23) & 0xff;
+#else
+    union { float f; int i; } cv; cv.f = amax;
+    const int ebits = (cv.i >> 23) & 0xff;
+#endif
+    float down = 1.0f, up = 1.0f;
+    if (ebits >= 1 && ebits <= 253) {
+#if defined(__CUDA_ARCH__)
+        down = __int_as_float((254 - ebits) << 23);
+        up   = __int_as_float(ebits << 23);
+#else
+        union { float f; int i; } a, b; a.i = (254 - ebits) << 23; b.i = ebits << 23;
+        down = a.f; up = b.f;
+#endif
+    }
+    // column vectors of the scaled matrix
+    float b0[3] = {A[0] * down, A[3] * down, A[6] * down};
+    float b1[3] = {A[1] * down, A[4] * down, A[7] * down};
+    float b2[3] = {A[2] * down, A[5] * down, A[8] * down};
+    float v0[3] = {1.f, 0.f, 0.f}, v1[3] = {0.f, 1.f, 0.f}, v2[3] = {0.f, 0.f, 1.f};
+#pragma unroll 1
+    for (int sweep = 0; sweep < kJacobiSweeps; ++sweep) {
+        jacobi_pair(b0, b1, v0, v1);
+        jacobi_pair(b0, b2, v0, v2);
+        jacobi_pair(b1, b2, v1, v2);
+    }
+    float n0 = fmaf(b0[0], b0[0], fmaf(b0[1], b0[1], b0[2] * b0[2]));
+    float n1 = fmaf(b1[0], b1[0], fmaf(b1[1], b1[1], b1[2] * b1[2]));
+    float n2 = fmaf(b2[0], b2[0], fmaf(b2[1], b2[1], b2[2] * b2[2]));
+    rot_swap(n0 < n1, b0, b1, v0, v1, n0, n1);
+    rot_swap(n0 < n2, b0, b2, v0, v2, n0, n2);
+    rot_swap(n1 < n2, b1, b2, v1, v2, n1, n2);
+
+    // left vectors: u0 = b0/|b0|, u1 = normalised (b1 - (b1.u0)u0), u2 = u0 x u1
+    float u0[3], u1[3], u2[3];
+    const float sig0 = sqrt_rn(n0);
+    if (sig0 > 0.0f) {
+        const float inv = div_rn(1.0f, sig0);
+        u0[0] = b0[0] * inv; u0[1] = b0[1] * inv; u0[2] = b0[2] * inv;
+    } else {
+        u0[0] = 1.f; u0[1] = 0.f; u0[2] = 0.f;
+    }
+    const float p = fmaf(b1[0], u0[0], fmaf(b1[1], u0[1], b1[2] * u0[2]));
+    float w[3] = {fmaf(-p, u0[0], b1[0]), fmaf(-p, u0[1], b1[1]), fmaf(-p, u0[2], b1[2])};
+    float nw = fmaf(w[0], w[0], fmaf(w[1], w[1], w[2] * w[2]));
+    if (!(nw > 1e-30f)) {
+        // rank <= 1: any unit vector orthogonal to u0 (axis least aligned with u0)
+        const float a0 = fabsf(u0[0]), a1 = fabsf(u0[1]), a2 = fabsf(u0[2]);
+        const int k = (a1 <= a0 && a1 <= a2) ? 1 : ((a2 <= a0 && a2 <= a1) ? 2 : 0);
+        const float uk = (k == 0) ? u0[0] : ((k == 1) ? u0[1] : u0[2]);
+        w[0] = ((k == 0) ? 1.f : 0.f) - uk * u0[0];
+        w[1] = ((k == 1) ? 1.f : 0.f) - uk * u0[1];
+        w[2] = ((k == 2) ? 1.f : 0.f) - uk * u0[2];
+        nw = fmaf(w[0], w[0], fmaf(w[1], w[1], w[2] * w[2]));
+    }
+    {
+        const float inv = div_rn(1.0f, sqrt_rn(nw));
+        u1[0] = w[0] * inv; u1[1] = w[1] * inv; u1[2] = w[2] * inv;
+    }
+    u2[0] = fmaf(u0[1], u1[2], -u0[2] * u1[1]);
+    u2[1] = fmaf(u0[2], u1[0], -u0[0] * u1[2]);
+    u2[2] = fmaf(u0[0], u1[1], -u0[1] * u1[0]);
+
+    s[0] = sig0 * up;
+    s[1] = fmaf(b1[0], u1[0], fmaf(b1[1], u1[1], b1[2] * u1[2])) * up;
+    s[2] = fmaf(b2[0], u2[0], fmaf(b2[1], u2[1], b2[2] * u2[2])) * up;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        U[3 * i + 0] = u0[i]; U[3 * i + 1] = u1[i]; U[3 * i + 2] = u2[i];
+        V[3 * i + 0] = v0[i]; V[3 * i + 1] = v1[i]; V[3 * i + 2] = v2[i];
+    }
+    return finite;
+}
+
+// R = U diag(d0,d1,d2) V^T  (row-major)
+SUHPE_HD void u_diag_vt(const float* U, const float* V, float d0, float d1, float d2, float* R) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = U[3 * i + 0] * d0, b = U[3 * i + 1] * d1, c = U[3 * i + 2] * d2;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            R[3 * i + j] = fmaf(a, V[3 * j + 0], fmaf(b, V[3 * j + 1], c * V[3 * j + 2]));
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Matrix-Fisher quadrature.
+//
+// I0e(a) = exp(-a) I0(a), a >= 0, by the reference's two polynomials:
+//   a <= 3.75 : P6((a/3.75)^2) * exp(-a)          (A&S 9.8.1)
+//   a >  3.75 : P8(3.75/a) / sqrt(a)              (A&S 9.8.2)
+// The powers of 3.75 are folded into the coefficients (poly in a^2 resp. 1/a),
+// and exp(-a) of the small branch is NOT applied here: the caller merges it
+// into the one exponential per node.
+// ----------------------------------------------------------------------------
+constexpr float kBesselSwitch = 3.75f;
+
+constexpr double cpow(double b, int n) { double r = 1.0; for (int i = 0; i < n; ++i) r *= b; return r; }
+// reference coefficient (a Python float stored into an fp32 tensor) folded with 3.75^k in double
+constexpr float fold_small(double coef, int k) { return (float)((double)(float)coef / cpow(3.75, k)); }
+constexpr float fold_large(double coef, int k) { return (float)((double)(float)coef * cpow(3.75, k)); }
+
+constexpr float kSm6 = fold_small(0.45813e-2, 12), kSm5 = fold_small(0.360768e-1, 10),
+                kSm4 = fold_small(0.2659732, 8),   kSm3 = fold_small(1.2067492, 6),
+                kSm2 = fold_small(3.0899424, 4),   kSm1 = fold_small(3.5156229, 2);
+constexpr float kLg8 = fold_large(0.392377e-2, 8),   kLg7 = fold_large(-0.1647633e-1, 7),
+                kLg6 = fold_large(0.2635537e-1, 6),  kLg5 = fold_large(-0.2057706e-1, 5),
+                kLg4 = fold_large(0.916281e-2, 4),   kLg3 = fold_large(-0.157565e-2, 3),
+                kLg2 = fold_large(0.225319e-2, 2),   kLg1 = fold_large(0.1328592e-1, 1),
+                kLg0 = fold_large(0.39894228, 0);
+
+SUHPE_HD float i0_small_poly(float a) {
+    // sum_i A_i (a/3.75)^(2i) as a polynomial in q = a^2
+    const float q = a * a;
+    float p = kSm6;
+    p = fmaf(p, q, kSm5);
+    p = fmaf(p, q, kSm4);
+    p = fmaf(p, q, kSm3);
+    p = fmaf(p, q, kSm2);
+    p = fmaf(p, q, kSm1);
+    p = fmaf(p, q, 1.0f);
+    return p;
+}
+
+// returns P8(3.75/a)/sqrt(a) as a polynomial in r = 1/a; one MUFU (rsqrt), r = rsqrt^2
+SUHPE_HD float i0e_large(float a) {
+    const float rs = mufu_rsqrt(a);
+    const float r = rs * rs;
+    float p = kLg8;
+    p = fmaf(p, r, kLg7);
+    p = fmaf(p, r, kLg6);
+    p = fmaf(p, r, kLg5);
+    p = fmaf(p, r, kLg4);
+    p = fmaf(p, r, kLg3);
+    p = fmaf(p, r, kLg2);
+    p = fmaf(p, r, kLg1);
+    p = fmaf(p, r, kLg0);
+    return p * rs;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// quadrature node i of 512 on [-1,1], rounded exactly like the reference:
+// fl(fl(i * fl(2/511)) - 1)   (src/fisher/torch_norm_factor.py:25-26)
+SUHPE_HD float quad_node(float i_as_float) {
+    return add_rn(mul_rn(i_as_float, (float)(2.0 / 511.0)), -1.0f);
+}
+
+// One family of the three Bessel-product integrands:
+//   y(x) = I0e(fd (1-x)) * I0e(fs (1+x)) * exp(c (x-1))
+// fam 0 (normaliser & d/ds1): fd=(s2-s3)/2 fs=(s2+s3)/2 c=s1+s3
+// fam 1 (d/ds2)             : fd=(s1-s3)/2 fs=(s1+s3)/2 c=s2+s3
+// fam 2 (d/ds3)             : fd=(s1-s2)/2 fs=(s1+s2)/2 c=s2+s3
+// (src/fisher/torch_norm_factor.py:33-63 with the cyclic shifts of :85-87).
+struct Family { float fd, fs, c; };
+
+SUHPE_HD void fisher_families(const float* s, Family* f) {
+    f[0].fd = 0.5f * (s[1] - s[2]); f[0].fs = 0.5f * (s[1] + s[2]); f[0].c = s[0] + s[2];
+    f[1].fd = 0.5f * (s[0] - s[2]); f[1].fs = 0.5f * (s[0] + s[2]); f[1].c = s[1] + s[2];
+    f[2].fd = 0.5f * (s[0] - s[1]); f[2].fs = 0.5f * (s[0] + s[1]); f[2].c = s[1] + s[2];
+}
+
+// Scalar node evaluation, any mix of branches (used by the divergent-lane path
+// of the kernel and by the host emulation).  u = 1-x, v = 1+x.
+SUHPE_HD float fisher_node(const Family& f, float u, float v) {
+    const float ad = fabsf(f.fd * u);
+    const float as = fabsf(f.fs * v);
+    float e = -f.c * u;          // c (x-1)
+    float pd, ps;
+    if (ad <= kBesselSwitch) { pd = i0_small_poly(ad); e -= ad; } else { pd = i0e_large(ad); }
+    if (as <= kBesselSwitch) { ps = i0_small_poly(as); e -= as; } else { ps = i0e_large(as); }
+    return pd * ps * mufu_ex2(e * kLog2e);
+}
+
+// Closing arithmetic once the four trapezoid sums are known.
+//   F  = sum_i w_i y0(x_i)        N0 = sum_i w_i x_i y0(x_i)
+//   N1 = sum_i w_i x_i y1(x_i)    N2 = sum_i w_i x_i y2(x_i)
+// f = 1/2 * (F * 2/511),  g_j = (1/2 * N_j * 2/511) / f   (torch_norm_factor.py:31,73,87-88)
+struct FisherStats { float logf, logC, g[3], entropy; };
+
+SUHPE_HD FisherStats fisher_finish(const float* s, float F, float N0, float N1, float N2) {
+    FisherStats o;
+    const float f = div_rn(F, 511.0f);
+    o.g[0] = div_rn(div_rn(N0, 511.0f), f);
+    o.g[1] = div_rn(div_rn(N1, 511.0f), f);
+    o.g[2] = div_rn(div_rn(N2, 511.0f), f);
+    o.logf = logf(f);
+    o.logC = o.logf + (s[0] + s[1] + s[2]);
+    // H = log f + sum_j s_j (1 - g_j): algebraic collapse of the reference's
+    // Fisher->Bingham->autograd chain (src/fisher/fisher_utils.py:70-81)
+    o.entropy = o.logf + fmaf(s[0], 1.0f - o.g[0], fmaf(s[1], 1.0f - o.g[1], s[2] * (1.0f - o.g[2])));
+    return o;
+}
+
+// ----------------------------------------------------------------------------
+// Entropy -> radix key with numpy.sort's total order: ascending, -0 == +0,
+// NaN last (src/agent.py:405).
+// ----------------------------------------------------------------------------
+SUHPE_HD uint32_t entropy_key(float e) {
+    if (e != e) return 0xFFFFFFFFu;
+    if (e == 0.0f) e = 0.0f;  // -0 -> +0
+#if defined(__CUDA_ARCH__)
+    uint32_t u = __float_as_uint(e);
+#else
+    union { float f; uint32_t u; } c; c.f = e; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+SUHPE_HD float key_entropy(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    if (k == 0xFFFFFFFFu) u = 0x7FC00000u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+// ----------------------------------------------------------------------------
+// Error metrics.
+// ----------------------------------------------------------------------------
+// (pitch, yaw, roll) in radians, src/utils.py:232-260 incl. the arithmetic blend
+// with the singular flag taken before the full-range flip.
+SUHPE_HD void euler_from_rotation(const float* R, bool full_range, float* out) {
+    const float r00 = R[0], r10 = R[3];
+    float sy = sqrt_rn(add_rn(mul_rn(r00, r00), mul_rn(r10, r10)));
+    const float sing = (sy < 1e-6f) ? 1.0f : 0.0f;
+    if (full_range && r00 < 0.0f) sy = -sy;
+    const float x = atan2f(R[7], R[8]);
+    const float y = atan2f(-R[6], sy);
+    const float z = atan2f(r10, r00);
+    const float xs = atan2f(-R[5], R[4]);
+    const float zs = r10 * 0.0f;
+    const float keep = 1.0f - sing;
+    out[0] = add_rn(mul_rn(x, keep), mul_rn(xs, sing));
+    out[1] = add_rn(mul_rn(y, keep), mul_rn(y, sing));
+    out[2] = add_rn(mul_rn(z, keep), mul_rn(zs, sing));
+}
+
+// mean_3 | euler * 180 / pi - gt_euler_deg |   (src/agent.py:452-454)
+SUHPE_HD float euler_mae_degrees(const float* euler_rad, const float* gt_deg) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float deg = div_rn(mul_rn(euler_rad[k], 180.0f), 3.14159265358979323846f);
+        acc = add_rn(acc, fabsf(deg - gt_deg[k]));
+    }
+    return div_rn(acc, 3.0f);
+}
+
+// trace(Rp Rg^T) = sum_ij Rp_ij Rg_ij
+SUHPE_HD float relative_trace(const float* Rp, const float* Rg) {
+    float d0 = fmaf(Rp[0], Rg[0], fmaf(Rp[1], Rg[1], Rp[2] * Rg[2]));
+    float d1 = fmaf(Rp[3], Rg[3], fmaf(Rp[4], Rg[4], Rp[5] * Rg[5]));
+    float d2 = fmaf(Rp[6], Rg[6], fmaf(Rp[7], Rg[7], Rp[8] * Rg[8]));
+    return d0 + d1 + d2;
+}
+
+// pytorch3d acos_linear_extrapolation with bounds +-(1-1e-4), then degrees.
+// ok=false when the trace leaves [-1-1e-4, 3+1e-4] (pytorch3d raises ValueError).
+SUHPE_HD float geodesic_degrees(float trace, bool* ok) {
+    *ok = !(trace < -1.0f - 1e-4f) && !(trace > 3.0f + 1e-4f);
+    const float c = (trace - 1.0f) * 0.5f;
+    const float bound = (float)(1.0 - 1e-4);
+    const float slope = (float)(-1.0 / 0.014141782065918747);   // -1/sqrt(1-bound^2)
+    float ang;
+    if (c >= bound)        ang = fmaf(c - bound, slope, (float)0.014142253285269182);   // acos(bound)
+    else if (c <= -bound)  ang = fmaf(c + bound, slope, (float)3.1274504003045240);     // acos(-bound)
+    else                   ang = acosf(c);
+    return ang * (float)(180.0 / 3.14159265358979323846);
+}
+
+// ||I - Rp Rg^T||_F   (eval.py:93-98)
+SUHPE_HD float frobenius_to_identity(const float* Rp, const float* Rg) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float d = fmaf(Rp[3 * i], Rg[3 * j], fmaf(Rp[3 * i + 1], Rg[3 * j + 1], Rp[3 * i + 2] * Rg[3 * j + 2]));
+            const float e = ((i == j) ? 1.0f : 0.0f) - d;
+            acc = fmaf(e, e, acc);
+        }
+    return sqrt_rn(acc);
+}
+
+}  // namespace suhpe

@@ -1,0 +1,87 @@
+"""Drop-in for the reference's ``src/fisher/fisher_utils.py`` on CUDA tensors.
+
+Same names, arguments and return shapes; every function is ONE kernel launch
+(K1 or K2 of ``csrc/fisher_kernels.cu``) instead of the reference's CPU SVD
+round trips and hundreds of elementwise ops.  Differences that are deliberate:
+
+* inputs must be CUDA fp32 (the reference moves them to the CPU itself);
+* ``fisher_entropy`` / ``batch_torch_A_to_R`` return plain tensors without a
+  ``grad_fn`` (the agent uses them detached: src/agent.py:108,139,152);
+* ``vmf_loss`` / ``KL_Fisher`` / ``fisher_log_pdf`` are differentiable w.r.t. the
+  network output exactly like the reference (only the singular values enter
+  autograd there, fisher_utils.py:29-31): the backward multiplies the per-sample
+  gradient the forward launch already produced.
+"""
+import torch
+
+from .. import _ops
+
+
+class _FisherNLL(torch.autograd.Function):
+    """nll_i = -<A_i,R_i> + overreg*logC(S_i);  d nll_i/dA_i from the same launch."""
+
+    @staticmethod
+    def forward(ctx, A, R, overreg, want_rot):
+        need_grad = ctx.needs_input_grad[0]
+        out = _ops.fisher_fused(A, R, overreg, nll=True, grad=need_grad, rot=want_rot, what="KL_Fisher")
+        if need_grad:
+            ctx.save_for_backward(out["grad"])
+        ctx.a_shape = A.shape
+        rot = out.get("rot")
+        if rot is None:
+            rot = torch.empty(0, device=A.device)
+        ctx.mark_non_differentiable(rot)
+        return out["nll"], rot
+
+    @staticmethod
+    def backward(ctx, g_nll, _g_rot):
+        (grad,) = ctx.saved_tensors
+        return (grad * g_nll.reshape(-1, 1)).view(ctx.a_shape), None, None, None
+
+
+def vmf_loss(net_out, R, overreg=1.05):
+    """(loss (b,), Rest (b,3,3))  -- reference fisher_utils.py:14-18."""
+    A = net_out.view(-1, 3, 3)
+    loss_v, Rest = _FisherNLL.apply(A, R, float(overreg), True)
+    return loss_v, Rest
+
+
+def KL_Fisher(A, R, overreg=1.05):
+    """Matrix-Fisher NLL (b,) -- reference fisher_utils.py:21-36."""
+    loss_v, _ = _FisherNLL.apply(A, R, float(overreg), False)
+    return loss_v
+
+
+def batch_torch_A_to_R(A):
+    """Proper-SVD projection onto SO(3), (b,9)|(b,3,3) -> (b,3,3)
+    -- reference fisher_utils.py:39-48."""
+    return _ops.proper_svd(A, rot=True, what="batch_torch_A_to_R")["rot"]
+
+
+def fisher_log_pdf(A, R):
+    """<A,R> - logC(S)  -- reference fisher_utils.py:51-67."""
+    return -KL_Fisher(A, R, overreg=1.0)
+
+
+def fisher_entropy(A):
+    """(b,9)|(b,3,3) -> (b,) entropy of the matrix-Fisher distribution
+    -- reference fisher_utils.py:70-81 (Fisher -> Bingham -> autograd chain, collapsed
+    to H = log f(s) + sum_j s_j (1 - g_j))."""
+    return _ops.fisher_fused(A, None, 1.0, entropy=True, what="fisher_entropy")["entropy"]
+
+
+def fisher_nll_entropy(net_out, R, overreg=1.05):
+    """Fused extra (no reference equivalent): NLL, projected rotation AND entropy of the
+    same batch from one launch -> (loss, Rest, entropy)."""
+    A = net_out.view(-1, 3, 3)
+    out = _ops.fisher_fused(A, R, overreg, nll=True, rot=True, entropy=True, what="fisher_nll_entropy")
+    return out["nll"], out["rot"], out["entropy"]
+
+
+def fisher_CE(A1, A2):
+    """Cross entropy between two matrix-Fisher distributions (reference
+    fisher_utils.py:84-99).  SURVEY.md section 8(f) ranks it 'next' (needs the quaternion
+    frames and a backward through U,V); not on the path built so far."""
+    raise NotImplementedError(
+        "fisher_CE is outside the hot path implemented in this round (SURVEY.md 8f-1); "
+        "use type_unsuper='nll' or the reference's fisher_CE")

@@ -1,0 +1,73 @@
+"""Host-buffer entry of the C ABI: the teacher-side filter step over a pool that lives
+in HOST memory (``suhpe_fisher_filter_host``).
+
+This is what a non-torch host (or ``bench.py``'s end-to-end leg) calls: pinned host
+arrays in, pinned host arrays out; chunks are copied H2D, run through the fused
+Fisher kernel (+ first radix histogram) and copied back D2H on alternating CUDA
+streams, then the percentile threshold and the keep-mask are produced on the
+device and copied back.  torch is used only to own the pinned buffers.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+from .agent import pool_index
+
+
+class FisherFilterPipeline:
+    def __init__(self, max_n, chunk=1 << 20, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("FisherFilterPipeline needs a CUDA device: semiuhpe_b200 has no CPU path")
+        self.device = torch.device("cuda", device)
+        self.max_n, self.chunk = int(max_n), int(chunk)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib().suhpe_pipeline_create(ctypes.byref(self._h), self.max_n, self.chunk),
+                        "pipeline_create")
+        self._out = None
+
+    def close(self):
+        if self._h:
+            _capi.lib().suhpe_pipeline_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _buffers(self, n, want_grad):
+        if self._out is None or self._out["n"] != n or (want_grad and self._out["grad"] is None):
+            self._out = dict(
+                n=n,
+                nll=torch.empty(n, dtype=torch.float32).pin_memory(),
+                grad=torch.empty((n, 9), dtype=torch.float32).pin_memory() if want_grad else None,
+                entropy=torch.empty(n, dtype=torch.float32).pin_memory(),
+                mask=torch.empty(n, dtype=torch.bool).pin_memory())
+        return self._out
+
+    def run(self, A_host, R_host, overreg=1.025, left_ratio=0.95, want_grad=True):
+        """A_host, R_host: CPU fp32 (n,9) tensors (pinned for full PCIe rate).
+        Returns dict(nll, grad, entropy, mask (CPU, pinned), threshold: float, kept: int)."""
+        for name, t in (("A_host", A_host), ("R_host", R_host)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError(f"{name} must be a contiguous CPU float32 tensor")
+        n = A_host.reshape(-1, 9).shape[0]
+        if n > self.max_n:
+            raise ValueError(f"pool of {n} exceeds the pipeline capacity {self.max_n}")
+        k = pool_index(n, left_ratio)
+        out = self._buffers(n, want_grad)
+        thr, kept = ctypes.c_float(), ctypes.c_uint64()
+        P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            code = _capi.check(_capi.lib().suhpe_fisher_filter_host(
+                self._h, P(A_host), P(R_host), n, float(overreg), k, P(out["nll"]), P(out["grad"]),
+                P(out["entropy"]), P(out["mask"]), ctypes.byref(thr), ctypes.byref(kept)), "fisher_filter_host")
+        if code & _capi.STATUS_NONFINITE:
+            raise torch.linalg.LinAlgError("fisher_filter_host: the input contains non-finite values")
+        res = dict(out)
+        res.update(threshold=thr.value, kept=int(kept.value),
+                   h2d_bytes=n * 72, d2h_bytes=n * (4 + 4 + 1 + (36 if want_grad else 0)))
+        return res

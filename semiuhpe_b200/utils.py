@@ -1,0 +1,38 @@
+"""Drop-in for the Euler helpers of the reference's ``src/utils.py`` (lines 202-300)."""
+import math
+
+import numpy as np
+import torch
+
+from . import _ops
+
+
+def compute_euler_angles_from_rotation_matrices(rotation_matrices, full_range=False, use_gpu=True, gpu_id=0):
+    """(b,3,3) -> (b,3) radians (pitch, yaw, roll)  -- src/utils.py:232-260.
+    One K4 launch instead of the reference's per-sample Python loop (:240-242).
+    ``use_gpu``/``gpu_id`` are accepted for signature compatibility; the result
+    lives on the input's CUDA device."""
+    R = rotation_matrices
+    if R.dim() == 3 and R.shape[1:] == (4, 4):
+        R = R[:, :3, :3]
+    return _ops.so3_metrics(R, full_range=full_range, euler=True)["euler"]
+
+
+def get_6DRepNet_Rot(x, y, z):
+    """R = Rz(z) Ry(y) Rx(x) from radians (host helper used to build labels, src/utils.py:204-226)."""
+    cx, sx, cy, sy, cz, sz = math.cos(x), math.sin(x), math.cos(y), math.sin(y), math.cos(z), math.sin(z)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz.dot(Ry.dot(Rx))
+
+
+def limit_angle(angle, pi=180.0):
+    """Wrap degrees into [-180, 180] (host scalar helper, src/utils.py:289-300)."""
+    if angle < -pi:
+        k = -2 * (int(angle / pi) // 2)
+        angle = angle + k * pi
+    if angle > pi:
+        k = 2 * ((int(angle / pi) + 1) // 2)
+        angle = angle - k * pi
+    return angle

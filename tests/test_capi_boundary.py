@@ -1,0 +1,100 @@
+"""The C-ABI boundary without a GPU: the library loads, exports exactly what
+include/semiuhpe_b200.h declares, the ctypes table matches the header, and the host
+side refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "semiuhpe_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = re.findall(r"\b(suhpe_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", text)
+    return {name: args for name, args in decls}
+
+
+def test_header_symbols_are_exported(built):
+    from semiuhpe_b200 import _build
+    out = subprocess.run(["nm", "-D", "--defined-only", _build.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (suhpe_[a-z0-9_]+)", out))
+    declared = set(declared_functions())
+    assert declared, "no declarations parsed"
+    assert declared == exported, f"header-only: {declared - exported}, library-only: {exported - declared}"
+
+
+def test_ctypes_table_matches_header(built):
+    from semiuhpe_b200 import _capi
+    decl = declared_functions()
+    assert set(_capi.SIGNATURES) == set(decl)
+    for name, args in decl.items():
+        n_args = 0 if args.strip() in ("", "void") else len(args.split(","))
+        assert len(_capi.SIGNATURES[name][1]) == n_args, name
+    handle = _capi.lib()                      # dlopen works without a GPU
+    assert handle.suhpe_abi_version() == 1
+    assert handle.suhpe_error_string(0) == b"ok"
+    assert handle.suhpe_error_string(_capi.EINVAL) == b"invalid argument"
+    # argument validation happens before any CUDA call
+    assert handle.suhpe_fisher_fused_f32(None, None, 5, 1.0, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
+    assert handle.suhpe_entropy_threshold_f32(None, 0, 0, None, None, None, None) == _capi.EINVAL
+    assert handle.suhpe_laplace_nll_f32(None, None, 1, None, 0, None, None, None, None, None, None) == _capi.EINVAL
+
+
+def test_sass_is_sm100a_only(built):
+    from semiuhpe_b200 import _build
+    out = subprocess.run(["cuobjdump", "-lelf", _build.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback(built):
+    """CPU tensors are an error, not a slow path."""
+    from semiuhpe_b200.fisher.fisher_utils import vmf_loss, fisher_entropy, batch_torch_A_to_R, fisher_CE
+    from semiuhpe_b200.laplace.rotation_laplace import NLL_loss
+    from semiuhpe_b200.agent import compute_err_deg_from_matrices, entropy_threshold, entropy_mask
+    A, R = torch.randn(4, 9), torch.eye(3).repeat(4, 1, 1)
+    for call in (lambda: vmf_loss(A, R), lambda: fisher_entropy(A), lambda: batch_torch_A_to_R(A),
+                 lambda: NLL_loss("RLaplace", A, R, R), lambda: compute_err_deg_from_matrices(R, R),
+                 lambda: entropy_threshold(torch.randn(10), 0.5), lambda: entropy_mask(torch.randn(10), 0.0)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+    with pytest.raises(NotImplementedError):
+        fisher_CE(A, A)
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under semiuhpe_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "semiuhpe_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "ref_shim" not in text and "/root/reference" not in text, f
+
+
+def test_pool_index_semantics():
+    from semiuhpe_b200.agent import pool_index
+    assert pool_index(128, 0.95) == 121
+    assert pool_index(2 ** 26, 0.95) == 63753420
+    assert pool_index(64000000, 0.95) == 60800000
+    assert pool_index(2 ** 26, 0.75) == 50331648
+    assert pool_index(10, 0.0) == 0
+    with pytest.raises(IndexError):
+        pool_index(128, 1.0)
+    with pytest.raises(IndexError):
+        pool_index(0, 0.5)
+
+
+def test_host_helpers_match_oracle(golden):
+    from oracle import so3_oracle as orc
+    from semiuhpe_b200 import utils
+    import numpy as np
+    g = golden("metrics")
+    assert [utils.limit_angle(a) for a in g["limit_in"]] == list(g["limit_out"])
+    np.testing.assert_allclose(utils.get_6DRepNet_Rot(0.3, -0.2, 1.1), orc.rot_from_euler(0.3, -0.2, 1.1), atol=1e-15)

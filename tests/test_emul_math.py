@@ -1,0 +1,132 @@
+"""The per-sample DEVICE arithmetic (semiuhpe_b200/csrc/so3_math.cuh) compiled for the
+host (tests/emul) against the oracle/golden vectors -- catches algorithmic errors in
+the SVD, the quadrature and the metrics without a GPU.  MUFU approximations are
+replaced by libm on the host, so the tight parity gate is the GPU suite."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ATOL, RTOL, assert_close, grad_rel_err, no_worse_than_reference
+from oracle import so3_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def emul(built):
+    return ctypes.CDLL(os.path.join(HERE, "emul", "libemul.so"))
+
+
+def run_fisher(emul, A, R, overreg):
+    A = np.ascontiguousarray(A.reshape(-1, 9), np.float32)
+    R = np.ascontiguousarray(R.reshape(-1, 9), np.float32)
+    n = len(A)
+    o = {k: np.zeros(s, np.float32) for k, s in dict(nll=n, grad=(n, 9), rot=(n, 9), ent=n, logC=n, S=(n, 3), G=(n, 3)).items()}
+    emul.emul_fisher(P(A), P(R), ctypes.c_long(n), ctypes.c_float(overreg), P(o["nll"]), P(o["grad"]), P(o["rot"]),
+                     P(o["ent"]), P(o["logC"]), P(o["S"]), P(o["G"]))
+    return o
+
+
+def test_quadrature_nodes_bitwise(emul):
+    x = np.zeros(512, np.float32)
+    emul.emul_quad_nodes(P(x))
+    ref, _ = orc.quad_nodes(torch.float32)
+    np.testing.assert_array_equal(x, ref.numpy().ravel())
+
+
+def test_bessel_polynomials(emul):
+    a = np.concatenate([np.linspace(0, 3.75, 2000), np.linspace(3.75, 400, 4000), [1e-8, 3.7499, 3.7501]]).astype(np.float32)
+    out = np.zeros_like(a)
+    emul.emul_i0e(P(a), ctypes.c_long(len(a)), P(out))
+    ref = orc.i0e(torch.from_numpy(a)).numpy()
+    np.testing.assert_allclose(out, ref, rtol=1e-6, atol=0)
+
+
+def test_fisher_against_golden(emul, golden):
+    g = golden("fisher")
+    o = run_fisher(emul, g["A"], g["R"], float(g["overreg"]))
+    names = g["names"]
+    regime = np.isin(names, ["generic1", "generic10", "generic30", "realistic", "neardegenerate"])
+    assert_close(o["nll"][regime], g["nll"][regime], RTOL, ATOL, "nll")
+    assert_close(o["ent"][regime], g["entropy"][regime], RTOL, ATOL, "entropy")
+    assert_close(o["logC"][regime], g["logC"][regime], RTOL, ATOL, "logC")
+    np.testing.assert_allclose(o["S"][regime], g["S"][regime], rtol=2e-6, atol=2e-6)
+    well = np.isin(names, ["generic1", "generic10", "generic30", "realistic"])
+    assert grad_rel_err(o["grad"][well], g["grad"][well]).max() < 1e-5
+    assert grad_rel_err(o["grad"][names == "neardegenerate"], g["grad"][names == "neardegenerate"]).max() < 1e-4
+    # rotation: conditioning ~ eps*s1/(s2+s3); generic rows are well conditioned
+    assert np.abs(o["rot"][well] - g["Rest"][well].reshape(-1, 9)).max() < 1e-5
+    # large singular values: no worse than the reference against exact arithmetic
+    A64 = torch.from_numpy(g["A"]).double()
+    ent64 = orc.fisher_entropy_closed_form(A64).numpy()
+    edge = ~regime
+    assert no_worse_than_reference(o["ent"][edge], g["entropy"][edge], ent64[edge], slack=2.0, floor=2e-6).all()
+    zero = list(names).index("zero")
+    assert o["nll"][zero] == 0 and o["ent"][zero] == 0
+    np.testing.assert_array_equal(o["rot"][zero], np.eye(3, dtype=np.float32).ravel())
+    np.testing.assert_allclose(o["grad"][zero], -np.eye(3).ravel(), atol=1e-6)
+
+
+def test_svd_properties(emul):
+    rng = np.random.default_rng(0)
+    n = 20000
+    A = np.concatenate([rng.standard_normal((n, 3, 3)) * s for s in (1e-20, 1e-3, 1.0, 30.0, 1e20)]).astype(np.float32)
+    A9 = np.ascontiguousarray(A.reshape(-1, 9))
+    m = len(A9)
+    R, S, U, V = (np.zeros((m, k), np.float32) for k in (9, 3, 9, 9))
+    ok = np.zeros(m, np.int32)
+    emul.emul_proper_svd(P(A9), ctypes.c_long(m), P(R), P(S), P(U), P(V), P(ok))
+    assert ok.all()
+    U3, V3, R3 = U.reshape(-1, 3, 3).astype(np.float64), V.reshape(-1, 3, 3).astype(np.float64), R.reshape(-1, 3, 3).astype(np.float64)
+    scale = np.abs(A).reshape(m, -1).max(1)
+    rec = np.einsum("nij,nj,nkj->nik", U3, S.astype(np.float64), V3)
+    assert (np.abs(rec - A).reshape(m, -1).max(1) / scale).max() < 3e-6
+    assert np.abs(np.einsum("nij,nkj->nik", R3, R3) - np.eye(3)).max() < 3e-6
+    assert np.abs(np.linalg.det(R3) - 1).max() < 5e-6          # det(R) = +1 always
+    assert np.abs(np.linalg.det(U3) - 1).max() < 5e-6 and np.abs(np.linalg.det(V3) - 1).max() < 5e-6
+    # sign convention: sign(S2) == sign(det A) (reference: det(U V^T) of LAPACK's factors)
+    detA = np.linalg.det(A.astype(np.float64) / scale[:, None, None])
+    clear = np.abs(detA) > 1e-4
+    assert np.array_equal(np.sign(S[clear, 2]), np.sign(detA[clear]))
+    sv = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    assert (np.abs(np.abs(S) - sv).max(1) / scale).max() < 3e-6
+    # non-finite input is flagged
+    bad = np.full((2, 9), np.nan, np.float32); bad[1] = np.inf
+    ok2 = np.ones(2, np.int32)
+    emul.emul_proper_svd(P(bad), ctypes.c_long(2), P(R), P(S), P(U), P(V), P(ok2))
+    assert not ok2.any()
+
+
+def test_keys_follow_numpy_sort_order(emul, golden):
+    e = golden("select")["ties"].copy()
+    k = np.zeros(len(e), np.uint32)
+    back = np.zeros(len(e), np.float32)
+    emul.emul_keys(P(e), ctypes.c_long(len(e)), P(k), P(back))
+    order = np.argsort(k, kind="stable")
+    np.testing.assert_array_equal(np.sort(e), e[order] + 0.0)       # NaN last, -0 == +0
+    np.testing.assert_array_equal(back[~np.isnan(e)], e[~np.isnan(e)] + 0.0)
+    assert np.isnan(back[np.isnan(e)]).all()
+
+
+def test_metrics_against_golden(emul, golden):
+    g = golden("metrics")
+    n = len(g["R_pd"])
+    for Rp, full, key in ((g["R_pd"], 0, "euler_pd"), (g["R_full"], 0, "euler_full_false"), (g["R_full"], 1, "euler_full_true")):
+        Rp9 = np.ascontiguousarray(Rp.reshape(-1, 9)); Rg9 = np.ascontiguousarray(g["R_gt"].reshape(-1, 9))
+        ge = np.ascontiguousarray(g["gt_euler"])
+        geo, frob, mae = (np.zeros(n, np.float32) for _ in range(3))
+        eul = np.zeros((n, 3), np.float32); ok = np.zeros(n, np.int32)
+        emul.emul_metrics(P(Rp9), P(Rg9), P(ge), ctypes.c_long(n), full, P(geo), P(frob), P(eul), P(mae), P(ok))
+        np.testing.assert_allclose(eul, g[key], rtol=0, atol=2e-6)
+        assert ok.all()
+        if key == "euler_pd":
+            np.testing.assert_allclose(mae, g["mae"], rtol=1e-5, atol=2e-4)
+            np.testing.assert_allclose(geo, g["geodesic_deg"], rtol=1e-4, atol=2e-3)
+            np.testing.assert_allclose(frob, g["frob"], rtol=1e-4, atol=1e-6)
+        else:
+            np.testing.assert_allclose(geo, g["geodesic_deg_full"], rtol=1e-4, atol=2e-3)
+            np.testing.assert_allclose(frob, g["frob_full"], rtol=1e-5, atol=1e-6)

@@ -1,0 +1,134 @@
+"""K2L (rotation-Laplace NLL fwd+bwd) and K4 (error metrics) parity."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, grad_rel_err, no_worse_than_reference, random_rotations
+from oracle import so3_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# The reference's own fp32 noise on this loss is 1.7e-5 relative for the NLL and ~6e-4 for the
+# gradient (cancellation in sum(s) - tr(A^T R)), so parity with its fp32
+# output is checked at 5e-5 / 2e-3 AND we must be no further from exact arithmetic than it is.
+LAP_RTOL, LAP_ATOL, LAP_GRAD = 5e-5, 5e-5, 2e-3
+
+
+def test_laplace_golden_small_batch_path(cuda, golden):
+    from semiuhpe_b200.laplace.rotation_laplace import NLL_loss, analytical_mode, log_pdf
+    g = golden("laplace")
+    A, R, grids = (torch.from_numpy(g[k]).to(cuda) for k in ("A", "R", "grids"))
+    leaf = A.clone().requires_grad_(True)
+    losses, mode = NLL_loss("RLaplace", leaf, R, grids)
+    losses.sum().backward()
+    assert losses.shape == (len(A),) and mode.shape == (len(A), 3, 3)
+    assert_close(losses.detach().cpu().numpy(), g["nll"], LAP_RTOL, LAP_ATOL, "laplace nll")
+    assert grad_rel_err(leaf.grad.cpu().numpy(), g["grad"]).max() < LAP_GRAD
+    A64, R64, g64 = (torch.from_numpy(g[k]).double() for k in ("A", "R", "grids"))
+    l64 = A64.clone().requires_grad_(True)
+    nll64, _ = orc.laplace_nll("RLaplace", l64, R64, g64)
+    nll64.sum().backward()
+    assert no_worse_than_reference(losses.detach().cpu().numpy(), g["nll"], nll64.detach().numpy(), 2.0, 5e-6).all()
+    ours_err = np.abs(leaf.grad.cpu().numpy().reshape(-1, 9) - l64.grad.numpy().reshape(-1, 9)).max(1)
+    ref_err = np.abs(g["grad"].reshape(-1, 9) - l64.grad.numpy().reshape(-1, 9)).max(1)
+    assert (ours_err <= 2 * ref_err + 1e-6 * (1 + np.abs(l64.grad.numpy()).reshape(-1, 9).max(1))).all()
+    well = (g["A"].reshape(-1, 9).std(1) > 0.5)
+    assert np.abs(mode.cpu().numpy() - g["mode"])[well].max() < 2e-5
+    m2, s3 = analytical_mode(A, "RLaplace")
+    assert torch.equal(m2, mode) and torch.equal(s3.cpu(), torch.sign(torch.from_numpy(g["s3sign"])))
+    assert_close(log_pdf("RFisher", A, R, grids).cpu().numpy(), g["rfisher_logpdf"], 2e-5, 2e-5, "RFisher grid pdf")
+    dens = log_pdf("RLaplace", A[:4], grids, grids)
+    want = orc.grid_log_pdf("RLaplace", torch.from_numpy(g["A"][:4]), torch.from_numpy(g["grids"]), torch.from_numpy(g["grids"]))
+    assert dens.shape == (4, grids.shape[0])
+    assert_close(dens.cpu().numpy(), want.numpy(), 2e-4, 2e-4, "broadcast density")
+
+
+def test_laplace_large_batch_path_matches_small(cuda, golden):
+    """>= 148*256 samples switch to the thread-per-sample decomposition; both decompositions
+    and a multi-chunk grid (N > 4608) must agree with each other and with the oracle."""
+    from semiuhpe_b200 import _ops
+    g = golden("laplace")
+    grids = torch.from_numpy(g["grids"]).to(cuda)
+    n = 148 * 256 + 77
+    gen = torch.Generator().manual_seed(2)
+    A = (5 * torch.randn(n, 3, 3, generator=gen)).to(cuda)
+    R = random_rotations(n, gen).to(cuda)
+    big = _ops.laplace_nll(A, R, grids, grad=True, mode=True)
+    small = _ops.laplace_nll(A[:300], R[:300], grids, grad=True, mode=True)
+    assert_close(big["nll"][:300].cpu().numpy(), small["nll"].cpu().numpy(), 2e-6, 2e-6, "decompositions")
+    assert grad_rel_err(big["grad"][:300].cpu().numpy(), small["grad"].cpu().numpy()).max() < 2e-4
+    assert torch.equal(big["mode"][:300], small["mode"])
+    idx = torch.arange(n - 64, n)
+    ref, _ = orc.laplace_nll("RLaplace", A[idx].cpu(), R[idx].cpu(), torch.from_numpy(g["grids"]))
+    assert_close(big["nll"][idx].cpu().numpy(), ref.numpy(), LAP_RTOL, LAP_ATOL, "tail rows")
+    # multi-chunk grid: 3x the points = 3 shared-memory chunks; logF shifts by exactly log(1) (duplicates)
+    grid3 = torch.cat([grids, grids, grids])
+    tri = _ops.laplace_nll(A[:300], R[:300], grid3)
+    assert_close(tri["nll"].cpu().numpy(), small["nll"].cpu().numpy(), 2e-6, 2e-6, "chunked grid")
+
+
+def test_metrics_golden(cuda, golden):
+    from semiuhpe_b200.agent import compute_err_deg_from_matrices, eval_rotation_metrics
+    from semiuhpe_b200.utils import compute_euler_angles_from_rotation_matrices as euler
+    g = golden("metrics")
+    Rp, Rg, Rf, ge = (torch.from_numpy(g[k]).to(cuda) for k in ("R_pd", "R_gt", "R_full", "gt_euler"))
+    # atan2f/acosf on the device are ~2 ulp; 1e-6 rad absolute on angles in [-pi, pi]
+    np.testing.assert_allclose(euler(Rp).cpu().numpy(), g["euler_pd"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(euler(Rf, full_range=False).cpu().numpy(), g["euler_full_false"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(euler(Rf, full_range=True).cpu().numpy(), g["euler_full_true"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(compute_err_deg_from_matrices(Rp, Rg, ge).cpu().numpy(), g["mae"], rtol=1e-5, atol=2e-4)
+    # geodesic: acos amplifies fp32 rounding of the trace near 0 deg: d(angle)/d(trace) ~ 1/(2 sin)
+    np.testing.assert_allclose(compute_err_deg_from_matrices(Rp, Rg).cpu().numpy(), g["geodesic_deg"], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(compute_err_deg_from_matrices(Rf, Rg).cpu().numpy(), g["geodesic_deg_full"], rtol=1e-5, atol=2e-4)
+    ev = eval_rotation_metrics(Rp, Rg, ge)
+    abs_ref = np.abs(g["euler_pd"] * 180 / np.pi - g["gt_euler"])
+    np.testing.assert_allclose(ev["abs_err"].cpu().numpy(), abs_ref, rtol=1e-5, atol=2e-4)
+    p, y, r, m = orc.euler_mae_summary(abs_ref)
+    np.testing.assert_allclose([ev["pitch"].item(), ev["yaw"].item(), ev["roll"].item(), ev["mean"].item()], [p, y, r, m], rtol=1e-5)
+    ev2 = eval_rotation_metrics(Rf, Rg)
+    np.testing.assert_allclose(ev2["frobenius"].cpu().numpy(), g["frob_full"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ev2["frobenius_mean"].item(), g["frob_full"].mean(), rtol=1e-6)
+    np.testing.assert_allclose(ev2["geodesic_mean"].item(), g["geodesic_deg_full"].astype(np.float64).mean(), rtol=1e-5)
+    with pytest.raises(ValueError):
+        compute_err_deg_from_matrices(3 * torch.eye(3, device=cuda)[None], torch.eye(3, device=cuda)[None])
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 10007])
+def test_metrics_ragged(cuda, n):
+    from semiuhpe_b200 import _ops
+    gen = torch.Generator().manual_seed(n)
+    Rp, Rg = random_rotations(n, gen), random_rotations(n, gen)
+    ge = (torch.rand(n, 3, generator=gen) * 2 - 1) * 90
+    out = _ops.so3_metrics(Rp.to(cuda), Rg.to(cuda), ge.to(cuda), geo=True, frob=True, euler=True, abs_err=True, mae=True, sums=True)
+    np.testing.assert_allclose(out["euler"].cpu().numpy(), orc.euler_from_matrices(Rp).numpy(), atol=2e-6)
+    np.testing.assert_allclose(out["mae"].cpu().numpy(), orc.err_deg_from_matrices(Rp, Rg, ge).numpy(), rtol=1e-5, atol=2e-4)
+    np.testing.assert_allclose(out["geo"].cpu().numpy(), orc.geodesic_deg(Rp, Rg).numpy(), rtol=1e-5, atol=2e-3)
+    np.testing.assert_allclose(out["frob"].cpu().numpy(), orc.frobenius_identity_distance(Rp, Rg), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["sums"][0].item(), out["geo"].double().sum().item(), rtol=1e-12)
+    off = torch.cat([torch.zeros(1, 9), Rp.reshape(-1, 9)]).to(cuda)[1:]
+    assert torch.equal(_ops.so3_metrics(off, Rg.to(cuda), geo=True)["geo"], out["geo"])
+
+
+def test_metrics_full_size_properties(cuda):
+    """10 M pairs (BASELINE config 4): Euler angles of Rz Ry Rx(gt) recover gt; the geodesic
+    angle of a pair built with a known relative rotation recovers that angle."""
+    from semiuhpe_b200 import _ops
+    n = 10_000_000
+    gen = torch.Generator(device=cuda).manual_seed(4)
+    e = (torch.rand(n, 3, device=cuda, generator=gen) * 2 - 1) * 89.0
+    r = torch.deg2rad(e)
+    cx, sx, cy, sy, cz, sz = r[:, 0].cos(), r[:, 0].sin(), r[:, 1].cos(), r[:, 1].sin(), r[:, 2].cos(), r[:, 2].sin()
+    R = torch.stack([cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx,
+                     sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx,
+                     -sy, cy * sx, cy * cx], 1)
+    out = _ops.so3_metrics(R, R, e, geo=True, mae=True, euler=True, sums=True)
+    assert out["mae"].max().item() < 2e-3                        # degrees
+    assert (out["geo"] - 0.40507).abs().max().item() < 5e-3      # pytorch3d's acos extension at identity
+    theta = torch.rand(n, device=cuda, generator=gen) * 170 + 5
+    t = torch.deg2rad(theta)
+    Rz = torch.zeros(n, 9, device=cuda)
+    Rz[:, 0], Rz[:, 1], Rz[:, 3], Rz[:, 4], Rz[:, 8] = t.cos(), -t.sin(), t.sin(), t.cos(), 1.0
+    R2 = (R.view(n, 3, 3) @ Rz.view(n, 3, 3)).reshape(n, 9)
+    geo = _ops.so3_metrics(R2, R, geo=True, frob=True)
+    assert (geo["geo"] - theta).abs().max().item() < 5e-3
+    assert (geo["frob"] - 2 * (2 ** 0.5) * (t / 2).sin()).abs().max().item() < 1e-5

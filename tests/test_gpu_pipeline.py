@@ -1,0 +1,34 @@
+"""Host-buffer pipeline of the C ABI (suhpe_fisher_filter_host): identical results to the
+device-resident path, including ragged chunking."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_rotations
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,chunk", [(1000, 1 << 20), (100003, 4096), (300000, 65536)])
+def test_pipeline_matches_device_path(cuda, n, chunk):
+    from semiuhpe_b200 import _capi, _ops
+    from semiuhpe_b200.agent import pool_index
+    from semiuhpe_b200.host_pipeline import FisherFilterPipeline
+    gen = torch.Generator().manual_seed(n)
+    A = (10 * torch.randn(n, 9, generator=gen)).pin_memory()
+    R = random_rotations(n, gen).reshape(n, 9).pin_memory()
+    pipe = FisherFilterPipeline(max_n=n, chunk=chunk)
+    res = pipe.run(A, R, overreg=1.025, left_ratio=0.95)
+    dev = _ops.fisher_fused(A.to(cuda), R.to(cuda), 1.025, nll=True, grad=True, entropy=True)
+    assert torch.equal(res["nll"], dev["nll"].cpu())
+    assert torch.equal(res["grad"], dev["grad"].cpu())
+    assert torch.equal(res["entropy"], dev["entropy"].cpu())
+    e = res["entropy"].numpy()
+    k = pool_index(n, 0.95)
+    thr = np.sort(e)[k]
+    assert res["threshold"] == float(thr)
+    assert np.array_equal(res["mask"].numpy(), e < thr)
+    assert res["kept"] == int((e < thr).sum())
+    pipe.close()

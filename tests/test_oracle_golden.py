@@ -1,0 +1,140 @@
+"""The oracle (torch-CPU restatement) against the golden vectors generated from the
+unmodified reference, and -- when /root/reference is present -- against the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pytorch3d_restated as p3d
+from oracle import ref_shim
+from oracle import so3_oracle as orc
+
+
+def test_fisher_golden_bit_exact(golden):
+    g = golden("fisher")
+    A, R = torch.from_numpy(g["A"]), torch.from_numpy(g["R"])
+    leaf = A.clone().requires_grad_(True)
+    nll, Rest = orc.vmf_loss(leaf.view(-1, 9), R, overreg=float(g["overreg"]))
+    nll.sum().backward()
+    # same torch ops in the same order: identical up to BLAS/LAPACK thread-count effects
+    np.testing.assert_allclose(nll.detach().numpy(), g["nll"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(Rest.detach().numpy(), g["Rest"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(leaf.grad.numpy(), g["grad"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(orc.fisher_entropy(A).numpy(), g["entropy"], rtol=2e-6, atol=5e-6)
+    np.testing.assert_allclose(orc.fisher_log_pdf(A, R).detach().numpy(), g["logpdf"], rtol=2e-6, atol=2e-6)
+    S = torch.from_numpy(g["S"]).requires_grad_(True)
+    logc = orc.log_normaliser(S)
+    logc.sum().backward()
+    np.testing.assert_allclose(logc.detach().numpy(), g["logC"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(S.grad.numpy(), g["dlogC"], rtol=1e-6, atol=1e-7)
+
+
+def test_fisher_known_answers(golden):
+    """Identities and recorded edge outputs of the reference."""
+    g = golden("fisher")
+    names = list(g["names"])
+    row = lambda n: names.index(n)
+    assert g["nll"][row("zero")] == 0 and g["entropy"][row("zero")] == 0
+    np.testing.assert_array_equal(g["Rest"][row("zero")], np.eye(3, dtype=np.float32))
+    np.testing.assert_allclose(g["entropy"][row("eye10")], -4.566861, atol=2e-6)
+    np.testing.assert_allclose(g["nll"][row("diag10_5_-2")], -4.258536, atol=2e-6)
+    np.testing.assert_allclose(g["entropy"][row("diag300_200_100")], 7.026253, atol=1e-5)   # quadrature breakdown
+    z = torch.zeros(1, 3)
+    assert orc.log_normaliser(z).item() == 0.0
+    np.testing.assert_allclose(orc.i0e(torch.tensor([0.0, 1e-8, 3.75, 10.0, 100.0, -5.0])).numpy(),
+                               [1, 1, 0.2145, 0.1278, 0.0399, 0.1835], atol=5e-5)
+
+
+def test_entropy_closed_form_matches_chain(golden):
+    """H = log f + sum s_j (1-g_j) (what the kernel evaluates) == the reference's
+    Fisher->Bingham->autograd chain, in exact arithmetic."""
+    g = golden("fisher")
+    keep = np.isin(g["names"], ["generic1", "generic10", "realistic", "neardegenerate"])
+    A = torch.from_numpy(g["A"][keep])
+    closed64 = orc.fisher_entropy_closed_form(A.double()).numpy()
+    np.testing.assert_allclose(g["entropy"][keep], closed64, rtol=1e-5, atol=2e-5)
+    grad64 = orc.fisher_nll_grad_closed_form(A.double(), torch.from_numpy(g["R"][keep]).double(), float(g["overreg"]))
+    np.testing.assert_allclose(g["grad"][keep], grad64.numpy(), rtol=1e-4, atol=2e-6)
+
+
+def test_laplace_golden(golden):
+    g = golden("laplace")
+    A, R, grids = (torch.from_numpy(g[k]) for k in ("A", "R", "grids"))
+    leaf = A.clone().requires_grad_(True)
+    nll, mode = orc.laplace_nll("RLaplace", leaf, R, grids)
+    nll.sum().backward()
+    np.testing.assert_allclose(nll.detach().numpy(), g["nll"], rtol=5e-6, atol=5e-6)
+    np.testing.assert_allclose(mode.detach().numpy(), g["mode"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(leaf.grad.numpy(), g["grad"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(orc.grid_log_pdf("RFisher", A, R, grids).numpy(), g["rfisher_logpdf"], rtol=5e-6, atol=5e-6)
+    # the reference's own cross-check (rotation_laplace.py:121): grid Fisher ~ analytic Fisher
+    analytic = orc.fisher_log_pdf(A, R).detach().numpy()
+    small = np.abs(g["A"]).reshape(len(A), -1).max(1) < 4
+    assert np.abs(g["rfisher_logpdf"][small] - analytic[small]).max() < 0.05
+
+
+def test_select_golden(golden):
+    g = golden("select")
+    for pool, thr, idx in ((g["entropy"], g["thresholds"], g["indices"]), (g["ties"], g["ties_thresholds"], g["ties_indices"])):
+        for r, t, i in zip(g["ratios"], thr, idx):
+            got_t, got_i = orc.pool_threshold(pool, float(r))
+            assert got_i == i
+            assert (np.isnan(got_t) and np.isnan(t)) or got_t == t
+    t128, k128 = orc.pool_threshold(g["entropy"][:128], 0.95)
+    assert k128 == g["k128"] == 121 and t128 == g["thr128"]
+    mask, ratio = orc.keep_mask(torch.from_numpy(g["entropy"][:128]), float(t128))
+    assert np.array_equal(mask.numpy(), g["mask128"]) and int(mask.sum()) == 121
+    with pytest.raises(IndexError):
+        orc.pool_threshold(g["entropy"], 1.0)
+    # int(n*ratio) pins from SURVEY appendix C
+    assert int(128 * 0.95) == 121 and int(2 ** 26 * 0.95) == 63753420 and int(64000000 * 0.95) == 60800000
+
+
+def test_metrics_golden(golden):
+    g = golden("metrics")
+    Rp, Rg, Rf = (torch.from_numpy(g[k]) for k in ("R_pd", "R_gt", "R_full"))
+    ge = torch.from_numpy(g["gt_euler"])
+    np.testing.assert_array_equal(orc.euler_from_matrices(Rp).numpy(), g["euler_pd"])
+    np.testing.assert_array_equal(orc.euler_from_matrices(Rf, False).numpy(), g["euler_full_false"])
+    np.testing.assert_array_equal(orc.euler_from_matrices(Rf, True).numpy(), g["euler_full_true"])
+    np.testing.assert_allclose(orc.err_deg_from_matrices(Rp, Rg, ge).numpy(), g["mae"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(orc.err_deg_from_matrices(Rp, Rg).numpy(), g["geodesic_deg"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(orc.frobenius_identity_distance(Rp, Rg), g["frob"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal([orc.limit_angle(a) for a in g["limit_in"]], g["limit_out"])
+    # identical rotations: pytorch3d's linear acos extension gives 0.405 deg, not 0
+    np.testing.assert_allclose(g["geodesic_deg"][0], 0.40507, atol=1e-4)
+    with pytest.raises(ValueError):
+        p3d.so3_relative_angle(3 * torch.eye(3)[None], torch.eye(3)[None])
+
+
+def test_pytorch3d_restatement_is_consistent():
+    """PARITY UNPINNED (pytorch3d absent): internal consistency only."""
+    gen = torch.Generator().manual_seed(3)
+    q = torch.randn(64, 4, generator=gen)
+    q = q / q.norm(dim=-1, keepdim=True)
+    R = p3d.quaternion_to_matrix(q)
+    back = p3d.matrix_to_quaternion(R)
+    same = torch.minimum((back - q).abs().max(1)[0], (back + q).abs().max(1)[0])
+    assert same.max() < 1e-5
+    ang = p3d.so3_relative_angle(R, R)
+    assert torch.allclose(ang, torch.full_like(ang, 0.0070711), atol=5e-5)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_oracle_matches_live_reference():
+    ref = ref_shim.load()
+    gen = torch.Generator().manual_seed(11)
+    A = 8 * torch.randn(96, 3, 3, generator=gen)
+    q, _ = torch.linalg.qr(torch.randn(96, 3, 3, generator=gen))
+    q[:, :, 2] *= torch.det(q)[:, None]
+    R = q.contiguous()
+    a1, a2 = A.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    l1, r1 = ref.fisher_utils.vmf_loss(a1.view(-1, 9), R, overreg=1.025)
+    l2, r2 = orc.vmf_loss(a2.view(-1, 9), R, overreg=1.025)
+    l1.sum().backward(); l2.sum().backward()
+    assert torch.equal(l1, l2) and torch.equal(r1, r2) and torch.equal(a1.grad, a2.grad)
+    assert torch.equal(ref.fisher_utils.fisher_entropy(A), orc.fisher_entropy(A))
+    grids = torch.from_numpy(np.load(ref.grid_path()))
+    n1, m1 = ref.rotation_laplace.NLL_loss("RLaplace", A[:16], R[:16], grids)
+    n2, m2 = orc.laplace_nll("RLaplace", A[:16], R[:16], grids)
+    assert torch.equal(n1, n2) and torch.equal(m1, m2)
+    assert torch.equal(ref.euler_from_matrices(R, full_range=True, use_gpu=False), orc.euler_from_matrices(R, True))
