@@ -292,7 +292,8 @@ def run_ours(args):
     fused_ms = k0.elapsed_time(k1) / reps
     clocks = sampler.stop() if sampler else None
 
-    thr, _, kept_n = ws.read()
+    thr = ws.read()[0]
+    kept_n = int(kept.item())
     assert int(status.item()) == 0 and bool(torch.isfinite(nll).all()) and bool(torch.isfinite(ent).all())
     value = n_total * args.steps / (ms_total * 1e-3)
 

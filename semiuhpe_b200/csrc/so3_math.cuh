@@ -297,24 +297,71 @@ SUHPE_HD float quad_node(float i_as_float) {
 // fam 1 (d/ds2)             : fd=(s1-s3)/2 fs=(s1+s3)/2 c=s2+s3
 // fam 2 (d/ds3)             : fd=(s1-s2)/2 fs=(s1+s2)/2 c=s2+s3
 // (src/fisher/torch_norm_factor.py:33-63 with the cyclic shifts of :85-87).
-struct Family { float fd, fs, c; };
+// The exponentials are evaluated as ex2(e) with e in the log2 domain, built from
+// per-family constants so that the scalar path below and the packed f32x2 loop
+// bodies of the kernel perform bit-identical operations:
+//   d large : kd = -c*log2e              d small : kd = -(c*log2e + fd*log2e)
+//   e = kd*u,  and if s small  e = fma(-fs*log2e, v, e)
+struct Family {
+    float fd, fs;        // |half difference|, |half sum|  (Bessel arguments are fd*u, fs*v)
+    float ncl, ncdl;     // -c*log2e, -(c*log2e + fd*log2e)
+    float nfsl;          // -fs*log2e
+};
 
-SUHPE_HD void fisher_families(const float* s, Family* f) {
-    f[0].fd = 0.5f * (s[1] - s[2]); f[0].fs = 0.5f * (s[1] + s[2]); f[0].c = s[0] + s[2];
-    f[1].fd = 0.5f * (s[0] - s[2]); f[1].fs = 0.5f * (s[0] + s[2]); f[1].c = s[1] + s[2];
-    f[2].fd = 0.5f * (s[0] - s[1]); f[2].fs = 0.5f * (s[0] + s[1]); f[2].c = s[1] + s[2];
+SUHPE_HD Family make_family(float lo, float hi, float c) {
+    Family f;
+    f.fd = fabsf(0.5f * (hi - lo));
+    f.fs = fabsf(0.5f * (hi + lo));
+    const float cl = c * kLog2e;
+    f.ncl = -cl;
+    f.ncdl = -(cl + f.fd * kLog2e);
+    f.nfsl = -(f.fs * kLog2e);
+    return f;
 }
 
-// Scalar node evaluation, any mix of branches (used by the divergent-lane path
-// of the kernel and by the host emulation).  u = 1-x, v = 1+x.
+SUHPE_HD void fisher_families(const float* s, Family* f) {
+    f[0] = make_family(s[2], s[1], s[0] + s[2]);
+    f[1] = make_family(s[2], s[0], s[1] + s[2]);
+    f[2] = make_family(s[1], s[0], s[1] + s[2]);
+}
+
+// Scalar node evaluation, any mix of branches (generic lanes of the kernel, the
+// trapezoid end-point corrections and the host emulation).  u = 1-x, v = 1+x.
 SUHPE_HD float fisher_node(const Family& f, float u, float v) {
-    const float ad = fabsf(f.fd * u);
-    const float as = fabsf(f.fs * v);
-    float e = -f.c * u;          // c (x-1)
-    float pd, ps;
-    if (ad <= kBesselSwitch) { pd = i0_small_poly(ad); e -= ad; } else { pd = i0e_large(ad); }
-    if (as <= kBesselSwitch) { ps = i0_small_poly(as); e -= as; } else { ps = i0e_large(as); }
-    return pd * ps * mufu_ex2(e * kLog2e);
+    const float ad = f.fd * u;
+    const float as = f.fs * v;
+    const bool sd = ad <= kBesselSwitch, ss = as <= kBesselSwitch;
+    const float pd = sd ? i0_small_poly(ad) : i0e_large(ad);
+    const float ps = ss ? i0_small_poly(as) : i0e_large(as);
+    float e = (sd ? f.ncdl : f.ncl) * u;
+    e = fmaf(ss ? f.nfsl : 0.0f, v, e);
+    return (pd * ps) * mufu_ex2(e);
+}
+
+// Run descriptor of one family over the 8 node pairs-of-iterations (64 nodes each):
+// pairs [0,b1) are (d large, s small); [b1,m0) mixed; [m0,m1) uniform middle run
+// (both small if mid_ss else both large); [m1,b4) mixed; [b4,8) (d small, s large).
+// Classification is conservative by one node; mixed pairs are evaluated per lane,
+// so the result does not depend on it.  Packed as b1 | m0<<4 | m1<<8 | b4<<12 | mid_ss<<16.
+SUHPE_HD unsigned family_runs(const Family& f) {
+    const float nodes_per_unit = 255.5f;              // 511/2 nodes per unit of x
+    // nodes with index < id are large for d (a_d = fd*u, u ~ 2 - i*h decreasing);
+    // nodes with index <= is are small for s (a_s = fs*v, v ~ i*h increasing)
+    const float id = (2.0f - kBesselSwitch / f.fd) * nodes_per_unit;   // fd = 0 -> -inf
+    const float is = (kBesselSwitch / f.fs) * nodes_per_unit;          // fs = 0 -> +inf
+    const float inv64 = 1.0f / 64.0f;
+    const float dLf = fminf(fmaxf(floorf(id * inv64), 0.0f), 8.0f);
+    const float dSf = fminf(fmaxf(ceilf((id + 1.0f) * inv64), 0.0f), 8.0f);
+    const float sSf = fminf(fmaxf(floorf(is * inv64), 0.0f), 8.0f);
+    const float sLf = fminf(fmaxf(ceilf((is + 1.0f) * inv64), 0.0f), 8.0f);
+    const int dL = (int)dLf, dS = (int)dSf, sS = (int)sSf, sL = (int)sLf;
+    const int b1 = dL < sS ? dL : sS;
+    const int b4 = dS > sL ? dS : sL;
+    const bool mid_ss = dL <= sS;
+    int m0 = mid_ss ? dS : sL;
+    int m1 = mid_ss ? sS : dL;
+    if (m0 >= m1) { m0 = b1; m1 = b1; }
+    return (unsigned)b1 | ((unsigned)m0 << 4) | ((unsigned)m1 << 8) | ((unsigned)b4 << 12) | (mid_ss ? 1u << 16 : 0u);
 }
 
 // Closing arithmetic once the four trapezoid sums are known.

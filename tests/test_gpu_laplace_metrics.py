@@ -55,7 +55,7 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
     R = random_rotations(n, gen).to(cuda)
     big = _ops.laplace_nll(A, R, grids, grad=True, mode=True)
     small = _ops.laplace_nll(A[:300], R[:300], grids, grad=True, mode=True)
-    assert_close(big["nll"][:300].cpu().numpy(), small["nll"].cpu().numpy(), 2e-6, 2e-6, "decompositions")
+    assert_close(big["nll"][:300].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "decompositions")
     assert grad_rel_err(big["grad"][:300].cpu().numpy(), small["grad"].cpu().numpy()).max() < 2e-4
     assert torch.equal(big["mode"][:300], small["mode"])
     idx = torch.arange(n - 64, n)
@@ -64,7 +64,7 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
     # multi-chunk grid: 3x the points = 3 shared-memory chunks; logF shifts by exactly log(1) (duplicates)
     grid3 = torch.cat([grids, grids, grids])
     tri = _ops.laplace_nll(A[:300], R[:300], grid3)
-    assert_close(tri["nll"].cpu().numpy(), small["nll"].cpu().numpy(), 2e-6, 2e-6, "chunked grid")
+    assert_close(tri["nll"].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "chunked grid")
 
 
 def test_metrics_golden(cuda, golden):
