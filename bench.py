@@ -298,7 +298,7 @@ def run_ours(args):
     value = n_total * args.steps / (ms_total * 1e-3)
 
     # end-to-end leg on every rank at once (they share the host's PCIe/memory system), max over ranks
-    e2e = run_e2e(torch, dist, dev, n, args, world, rank)
+    e2e = None if args.no_e2e else run_e2e(torch, dist, dev, n, args, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -334,15 +334,15 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": step_launches, "roofline": roofline,
         "threshold": thr, "kept": kept_n,
     }
-    if world == 1:
+    if world == 1 and not args.no_cpu:
         v, cores, secs = time_cpu(args.cpu_sample, 1)
         line["cpu_baseline"] = {
             "value": v, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{args.cpu_sample} rotations of the same workload, 1 pass ({secs:.1f} s): oracle/so3_oracle.py "
                       "(torch-CPU restatement of the reference: vmf_loss fwd+bwd, fisher_entropy, numpy sort + mask), "
                       "all host threads"}
-        if not args.skip_extra:
-            line["extra"] = side_configs(torch, dev, _ops)
+    if world == 1 and not args.skip_extra:
+        line["extra"] = side_configs(torch, dev, _ops)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -462,6 +462,8 @@ def main():
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
     ap.add_argument("--skip-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -18,17 +18,17 @@ gen = torch.Generator(device=dev).manual_seed(0)
 rot = lambda m: _quat_to_matrix(torch.nn.functional.normalize(torch.randn(m, 4, device=dev, generator=gen), dim=1)).contiguous()
 A, R = 10 * torch.randn(n, 9, device=dev, generator=gen), rot(n)
 ws = _ops.SelectWorkspace(dev)
-for _ in range(3):
+for _ in range(1 if which == "others" else 3):
     if which in ("fisher", "all"):
         out = _ops.fisher_fused(A, R, 1.025, nll=True, grad=True, entropy=True, hist=ws.hist[0])
-    if which in ("select", "all"):
+    if which in ("select", "others", "all"):
         e = torch.randn(n, device=dev, generator=gen)
         entropy_mask(e, entropy_threshold(e, 0.95))
-    if which in ("laplace", "all"):
+    if which in ("laplace", "others", "all"):
         m = min(n, 1 << 18)
         grid = rot(4608)
         _ops.laplace_nll(A[:m] * 0.5, R[:m], grid, grad=True, mode=True)
-    if which in ("metrics", "all"):
+    if which in ("metrics", "others", "all"):
         ge = torch.rand(n, 3, device=dev, generator=gen) * 90
         _ops.so3_metrics(rot(n), R, ge, geo=True, frob=True, abs_err=True, sums=True)
 torch.cuda.synchronize()
