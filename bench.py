@@ -311,7 +311,7 @@ def run_ours(args):
     peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     probe = fp32_probe(torch, lib, dev, _capi)
     achieved_tflops = n * FLOP_PER_ROTATION / (fused_ms * 1e-3) / 1e12
-    peak_tflops = max(probe["ffma_tflops"], probe["ffma2_tflops"])
+    peak_tflops = max(probe.values())
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_gbs = n * HBM_BYTES_PER_ROTATION / (fused_ms * 1e-3) / 1e9
     roofline = {
@@ -355,7 +355,9 @@ def fp32_probe(torch, lib, dev, _capi):
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     blocks, iters = sms * 8, 4096
     out = {}
-    for variant, name, per in ((0, "ffma", 1), (1, "ffma2", 2), (2, "ffma_mufu", 1)):
+    for variant, name, per in ((0, "ffma", 1), (1, "ffma2", 2), (2, "ffma_mufu", 1), (3, "ffma2_ffma_mixed", 3),
+                               (4, "ffma2_plus_lop3", 2), (5, "ffma2_plus_iadd", 2),
+                               (6, "ffma2_imm_addend", 2), (7, "ffma2_bcast_scalar", 2)):
         for _ in range(2):
             _capi.check(lib.suhpe_fp32_probe(_capi.ptr(sink), variant, iters, blocks, _capi.stream()), "probe")
         torch.cuda.synchronize()

@@ -51,11 +51,19 @@ int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U
  *   Rout    = U V^T                                        batch_torch_A_to_R fisher_utils.py:39-48
  *   entropy = log f(S) + sum_j S_j (1 - g_j)               fisher_entropy fisher_utils.py:70-81
  *   logC, S (n,3), G = dlogC/dS (n,3)                      logC_F torch_norm_factor.py:66-92
- *   hist   += histogram of the top 11 bits of the entropy keys (first radix-select pass, fused)
+ *   hist   += histogram of the top 11 bits of the entropy keys (first radix-select pass, chained on
+ *             the same stream while the entropies are L2-resident; needs `entropy` non-NULL)
  * Rgt may be NULL (then nll = overreg*logC and grad has no -Rgt term); every output is nullable. */
 int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg,
                            float* nll, float* grad, float* Rout, float* entropy, float* logC,
                            float* S, float* G, uint64_t* hist, int* status, void* stream);
+
+/* Negligible-node cut of the K2 quadrature (process-wide setting; returns the previous value).
+ * Every integrand of src/fisher/torch_norm_factor.py:33-63 is bounded by exp(-c(1-x)), so the
+ * nodes far from x = 1 contribute less than 2^-bits of the normaliser sum in total; K2 skips
+ * that provably negligible prefix.  Default 26 (a quarter of an fp32 ulp of the sum: below what
+ * the reference's own fp32 torch.sum resolves); 0 evaluates all 512 nodes of every integral. */
+int suhpe_set_quadrature_cut_bits(int bits);
 
 /* K2 on given singular values: logC_F(S) and its backward G = dlogC/dS, entropy(S)
  * (src/fisher/torch_norm_factor.py:66-92 `logC_F`; S (n,3) sorted s1>=s2>=|s3| like every
@@ -106,8 +114,13 @@ int suhpe_so3_metrics_f32(const float* Rp, const float* Rg, const float* gt_eule
 
 /* FP32-pipe probe used by bench.py for the roofline denominator: launches `blocks` CTAs of
  * 256 threads, each thread running `iters` rounds of 8 independent dependent-FMA chains.
- * variant 0: scalar FFMA, 1: packed fma.rn.f32x2, 2: FFMA + 1 MUFU.EX2 per 8 FMA.
- * FMAs executed = blocks*256*iters*8*(variant==1 ? 2 : 1) * 8 (unroll). */
+ * variant 0: scalar FFMA, 1: packed fma.rn.f32x2, 2: FFMA + 1 MUFU.EX2 per 8 FMA,
+ * 3: packed and scalar chains interleaved 1:1, 4 / 5: every packed FMA followed by one LOP3 / IADD
+ * (does a 2-cycle FFMA2 leave an issue slot for the ALU pipe?).
+ * 6 / 7: packed FMA with an immediate addend / a broadcast scalar multiplier (K2's Horner operand forms).
+ * FMAs executed = blocks*256*iters*64*{1, 2, 1, 3, 2, 2, 2, 2}[variant].
+ * variant 100+v: K2 pass-body probe, 16 warps per CTA each running `iters` 128-node passes of run type
+ * v&3 (bit 2: no table loads, bit 3: no MUFU, bit 4: no slot mask); 46 packed FMA-pipe ops per pass. */
 int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks, void* stream);
 
 /* Host-buffer pipeline (what bench.py's e2e leg and a non-torch host would call):

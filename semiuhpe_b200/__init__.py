@@ -22,7 +22,7 @@ library must have been built (``__graft_entry__.build()``).
 """
 from . import _capi
 
-__all__ = ["set_error_checking", "error_checking", "library_path"]
+__all__ = ["set_error_checking", "error_checking", "library_path", "set_quadrature_cut_bits"]
 
 _CHECK = True
 
@@ -39,6 +39,13 @@ def set_error_checking(enabled):
 
 def error_checking():
     return _CHECK
+
+
+def set_quadrature_cut_bits(bits):
+    """Negligible-node cut of the Fisher quadrature (``suhpe_set_quadrature_cut_bits``): nodes
+    whose total contribution is provably below ``2**-bits`` of the normaliser sum are skipped.
+    Default 26; ``0`` evaluates all 512 nodes of every integral.  Returns the previous value."""
+    return _capi.lib().suhpe_set_quadrature_cut_bits(int(bits))
 
 
 def library_path():

@@ -21,6 +21,7 @@ i64, i32, u64, u32, f32 = ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctype
 SIGNATURES = {
     "suhpe_abi_version": (ctypes.c_int, []),
     "suhpe_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "suhpe_set_quadrature_cut_bits": (ctypes.c_int, [ctypes.c_int]),
     "suhpe_proper_svd_f32": (ctypes.c_int, [c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_fisher_fused_f32": (ctypes.c_int, [c_vp, c_vp, i64, f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_fisher_from_s_f32": (ctypes.c_int, [c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

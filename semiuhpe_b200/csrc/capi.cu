@@ -16,6 +16,9 @@ static_assert(sizeof(SelectState) == SUHPE_SELECT_STATE_BYTES, "SelectState layo
 static_assert(kHistBinsMax == SUHPE_HIST_BINS, "histogram width is part of the ABI");
 static_assert(kStatusNonFinite == SUHPE_STATUS_NONFINITE && kStatusTraceRange == SUHPE_STATUS_TRACE_RANGE, "status bits");
 
+// negligible-node cut of the Fisher quadrature (see cut_threshold in so3_math.cuh); process-wide
+static int g_cut_bits = 26;
+
 inline int rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
 inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -23,7 +26,83 @@ inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 template <int VARIANT>
 __global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters) {
     const float seed = 1.0f + 1e-7f * (float)(threadIdx.x + blockIdx.x);
-    if (VARIANT == 1) {
+    if (VARIANT == 6 || VARIANT == 7) {
+        // packed FMA whose addend is an immediate (6) or whose multiplier is a broadcast scalar register (7):
+        // the operand forms the Horner bodies of K2 use
+        unsigned long long x[8], a;
+        const float af = 0.9999f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(af));
+        float sc = 0.9999f + 1e-9f * (float)blockIdx.x;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const float v = seed + (float)c; asm("mov.b64 %0, {%1, %1};" : "=l"(x[c]) : "f"(v)); }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (VARIANT == 6) {
+                        asm volatile("{ .reg .b64 k; mov.b64 k, {0f38D1B717, 0f38D1B717}; fma.rn.f32x2 %0, %0, %1, k; }" : "+l"(x[c]) : "l"(a));
+                    } else {
+                        asm volatile("{ .reg .b64 k; mov.b64 k, {%1, %1}; fma.rn.f32x2 %0, %0, k, %2; }" : "+l"(x[c]) : "f"(sc), "l"(a));
+                    }
+                }
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[c])); acc += lo + hi; }
+        if (acc == 123.456f) sink[0] = acc;
+    } else if (VARIANT == 4 || VARIANT == 5) {
+        // 8 packed chains, each FFMA2 followed by one ALU (4: LOP3) or one MUFU-free FSEL-like (5: IADD) op:
+        // does a 2-cycle FFMA2 leave an issue slot for another pipe?
+        unsigned long long x[8], a, b;
+        unsigned int z[8];
+        const float af = 0.9999f, bf = 1e-4f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(af));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const float v = seed + (float)c; asm("mov.b64 %0, {%1, %1};" : "=l"(x[c]) : "f"(v)); z[c] = threadIdx.x + c; }
+        const unsigned int m = blockIdx.x | 0x55u;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[c]) : "l"(a), "l"(b));
+                    if (VARIANT == 4) asm volatile("xor.b32 %0, %0, %1;" : "+r"(z[c]) : "r"(m));
+                    else asm volatile("add.u32 %0, %0, %1;" : "+r"(z[c]) : "r"(m));
+                }
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[c])); acc += lo + hi + (float)z[c]; }
+        if (acc == 123.456f) sink[0] = acc;
+    } else if (VARIANT == 3) {
+        // 8 packed chains and 8 scalar chains interleaved: does the scalar FFMA find a free sub-pipe
+        // while FFMA2 occupies the other?
+        unsigned long long x[8], a, b;
+        float z[8];
+        const float af = 0.9999f, bf = 1e-4f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(af));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const float v = seed + (float)c; asm("mov.b64 %0, {%1, %1};" : "=l"(x[c]) : "f"(v)); z[c] = v; }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[c]) : "l"(a), "l"(b));
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(z[c]) : "f"(af), "f"(bf));
+                }
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[c])); acc += lo + hi + z[c]; }
+        if (acc == 123.456f) sink[0] = acc;
+    } else if (VARIANT == 1) {
         // 8 independent packed chains: x = x * a + b on (lo,hi) pairs
         unsigned long long x[8], a, b;
         const float af = 0.9999f, bf = 1e-4f;
@@ -73,7 +152,12 @@ namespace suhpe {
 cudaError_t launch_fp32_probe(float* sink, int variant, int iters, int blocks, cudaStream_t stream) {
     if (variant == 0) fp32_probe_kernel<0><<<blocks, 256, 0, stream>>>(sink, iters);
     else if (variant == 1) fp32_probe_kernel<1><<<blocks, 256, 0, stream>>>(sink, iters);
-    else fp32_probe_kernel<2><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 2) fp32_probe_kernel<2><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 3) fp32_probe_kernel<3><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 4) fp32_probe_kernel<4><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 5) fp32_probe_kernel<5><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 6) fp32_probe_kernel<6><<<blocks, 256, 0, stream>>>(sink, iters);
+    else fp32_probe_kernel<7><<<blocks, 256, 0, stream>>>(sink, iters);
     return cudaGetLastError();
 }
 }  // namespace suhpe
@@ -104,6 +188,13 @@ const char* suhpe_error_string(int code) {
     return "unknown";
 }
 
+int suhpe_set_quadrature_cut_bits(int bits) {
+    if (bits > 60) return SUHPE_EINVAL;
+    const int old = g_cut_bits;
+    g_cut_bits = bits < 0 ? 0 : bits;
+    return old;
+}
+
 int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U, float* V,
                          int* status, void* stream) {
     if (n < 0 || (n > 0 && !A)) return SUHPE_EINVAL;
@@ -114,11 +205,12 @@ int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U
 int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg,
                            float* nll, float* grad, float* Rout, float* entropy, float* logC,
                            float* S, float* G, uint64_t* hist, int* status, void* stream) {
-    if (n < 0 || (n > 0 && !A)) return SUHPE_EINVAL;
+    if (n < 0 || (n > 0 && !A) || (hist && !entropy)) return SUHPE_EINVAL;
     FisherArgs p{};
     p.A = A; p.Rgt = Rgt; p.n = (long long)n; p.overreg = overreg;
     p.nll = nll; p.grad = grad; p.Rout = Rout; p.entropy = entropy; p.logC = logC; p.S = S; p.G = G;
     p.hist = reinterpret_cast<unsigned long long*>(hist); p.status = status;
+    p.cut_bits = g_cut_bits;
     return rc(launch_fisher_fused(p, st(stream)));
 }
 
@@ -128,6 +220,7 @@ int suhpe_fisher_from_s_f32(const float* S, int64_t n, float* logC, float* G, fl
     FisherArgs p{};
     p.Sin = S; p.n = (long long)n; p.overreg = 1.0f;
     p.logC = logC; p.G = G; p.entropy = entropy; p.status = status;
+    p.cut_bits = g_cut_bits;
     return rc(launch_fisher_fused(p, st(stream)));
 }
 
@@ -207,7 +300,9 @@ int suhpe_so3_metrics_f32(const float* Rp, const float* Rg, const float* gt_eule
 }
 
 int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks, void* stream) {
-    if (!sink || iters < 1 || blocks < 1 || variant < 0 || variant > 2) return SUHPE_EINVAL;
+    if (!sink || iters < 1 || blocks < 1 || variant < 0) return SUHPE_EINVAL;
+    if (variant >= 100) return rc(launch_body_probe(sink, variant - 100, iters, blocks, st(stream)));
+    if (variant > 7) return SUHPE_EINVAL;
     return rc(launch_fp32_probe(sink, variant, iters, blocks, st(stream)));
 }
 
@@ -276,7 +371,7 @@ int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float
         a.nll = nll_host ? p->dNll[b] : nullptr;
         a.grad = grad_host ? p->dGrad[b] : nullptr;
         a.entropy = p->dEnt + base;
-        a.hist = p->dHist; a.status = p->dStatus;
+        a.hist = p->dHist; a.status = p->dStatus; a.cut_bits = g_cut_bits;
         CK(launch_fisher_fused(a, s));
         if (nll_host) CK(cudaMemcpyAsync(nll_host + base, p->dNll[b], (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
         if (grad_host) CK(cudaMemcpyAsync(grad_host + base * 9, p->dGrad[b], (size_t)cnt * 36, cudaMemcpyDeviceToHost, s));

@@ -9,33 +9,54 @@
 // (the reference runs ~1,980 + ~4,600 ATen ops and CPU LAPACK SVDs for these).
 //
 // Work decomposition (no tensor cores: nothing here is a dense contraction)
-//   phase 1  thread-per-sample : coalesced float4 tile load -> smem -> 9 regs,
-//            Hestenes SVD in registers, U/V parked in smem
-//   phase 2  warp-per-sample   : the 3 x 512 quadrature nodes of one sample are
-//            spread over the 32 lanes (16 iterations x 3 integrand families);
-//            consecutive nodes sit in consecutive lanes so the |a| <= 3.75
-//            polynomial switch is warp-uniform except in the <= 2 iterations
-//            that straddle a crossover; one MUFU.EX2 per node (the small-branch
-//            exp(-a) factors are merged into the tail exponential)
+//   phase 1  thread-per-sample : coalesced float4 tile load -> smem -> 9 regs, Hestenes SVD in
+//            registers, U/V parked in smem; per family the three uniform-type runs of the 512
+//            nodes, their constants and the negligible-node cut are derived ONCE by the owning
+//            thread and parked as 3 float4 (run words: so3_math.cuh)
+//   phase 2  warp-per-sample   : the warp replays the sample's runs; a pass covers 128 (or 64)
+//            consecutive node slots, lane l taking adjacent node pairs in the halves of f32x2
+//            registers.  Inside a run every node executes the same straight-line FFMA2 body: the
+//            large-argument Bessel branch needs no MUFU (1/u and log2 rsqrt(u) come from a
+//            shared-memory node table, 1/f and rsqrt(f) are per-sample constants), so one
+//            MUFU.EX2 per node is the only SFU work; slots outside a run are zeroed by selects
+//            on the ALU pipe
 //   phase 3  thread-per-sample : closing arithmetic, gradient
 //            -R_gt + overreg * U diag(g) V^T, entropy, staged float4 stores
+// Geometry: one persistent CTA of 20 warps per SM (<= 102 registers), 30 KB of node tables
+// shared by the CTA + 9 KB of scratch per warp in dynamic shared memory.
 #include "kernels.cuh"
 #include "so3_math.cuh"
+#include <cstddef>
 
 namespace suhpe {
 
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 20;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
 
-// per-warp shared scratch (floats)
+// per-warp shared scratch
 constexpr int kTileFloats = 32 * 9;              // one 32-sample tile of 3x3 records
 struct __align__(16) WarpScratch {
     float a[kTileFloats];      // A in  -> gradient out
     float r[kTileFloats];      // R_gt in -> projected rotation out
     float uv[18 * 32];         // U,V parked during the quadrature, [k][lane]
+    float4 desc[9 * 32];       // 3 families x 3 float4 of run constants, [f*3+q][sample]
+};
+
+// Node tables in shared memory, one float4 per PAIR of adjacent nodes (2m, 2m+1) so that a
+// lane's LDS.128 lands directly in two f32x2 register pairs.  A run body needs at most two
+// such loads per 64 nodes:
+//   LL  a = (iu, iv)  b = (u, Lu+Lv)        LS  a = (iu, v)  b = (u, Lu)
+//   SL  a = (iv, Lv)  b = (u)               SS  a = (u, v)
+// 288 entries: a run's last pass may read up to 31 pairs past node 511 (discarded).
+constexpr int kTabPairs = 288;
+struct __align__(16) QuadTables {
+    float4 LLa[kTabPairs], LLb[kTabPairs], LSa[kTabPairs], LSb[kTabPairs];
+    float4 SLa[kTabPairs], SSa[kTabPairs];
+    float2 SLb[kTabPairs];
+    NodeVals first, last;                     // nodes 0 and 511 (trapezoid half weights)
 };
 
 // coalesced load of `count` 3x3 records starting at `src` into smem `dst`
@@ -67,8 +88,8 @@ __device__ __forceinline__ void store_tile(float* __restrict__ dst, const float*
 }
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2) ------------------
-// One issue slot does two FMAs: the quadrature loop packs the two nodes a lane owns
-// in a pair of iterations (it, it+1) into one 64-bit register pair.
+// One issue slot carries two FMAs: a lane evaluates the two adjacent nodes (2m, 2m+1)
+// in the halves of one 64-bit register pair.  Scalars broadcast for free (R.F32 operand).
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
@@ -76,17 +97,14 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 dup(float x) { return pk(x, x); }
-__device__ __forceinline__ f2 rsq2(f2 a) { float lo, hi; upk(a, lo, hi); return pk(mufu_rsqrt(lo), mufu_rsqrt(hi)); }
 __device__ __forceinline__ f2 ex22(f2 a) { float lo, hi; upk(a, lo, hi); return pk(mufu_ex2(lo), mufu_ex2(hi)); }
 
-// same operation order as i0e_large / i0_small_poly in so3_math.cuh, two nodes at a time
-__device__ __forceinline__ f2 large2(f2 a) {
-    const f2 rs = rsq2(a);
-    const f2 r = mul2(rs, rs);
+// same operation order as large_poly / i0_small_poly in so3_math.cuh, two nodes at a time
+__device__ __forceinline__ f2 large2(f2 r) {
     f2 p = dup(kLg8);
     p = fma2(p, r, dup(kLg7)); p = fma2(p, r, dup(kLg6)); p = fma2(p, r, dup(kLg5)); p = fma2(p, r, dup(kLg4));
     p = fma2(p, r, dup(kLg3)); p = fma2(p, r, dup(kLg2)); p = fma2(p, r, dup(kLg1)); p = fma2(p, r, dup(kLg0));
-    return mul2(p, rs);
+    return p;
 }
 __device__ __forceinline__ f2 small2(f2 a) {
     const f2 q = mul2(a, a);
@@ -96,49 +114,115 @@ __device__ __forceinline__ f2 small2(f2 a) {
     return p;
 }
 
-// node table in shared memory: tab[pair][lane] = (u_lo, u_hi, v_lo, v_hi) for the nodes
-// 64*pair + lane (lo) and 64*pair + 32 + lane (hi);  u = 1-x, v = 1+x
-struct __align__(16) NodePair { f2 u, v; };
+struct RunConsts { float fd, fs, ifd, ifs, k1L, k1S, k2; };
 
-enum RunType { kLS = 0, kLL = 1, kSS = 2, kSL = 3, kMixed = 4 };
+// accumulate in place (keeps the accumulators pinned to one register pair)
+__device__ __forceinline__ void acc_add2(f2& acc, f2 y) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(y)); }
+__device__ __forceinline__ void acc_fma2(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 
-struct FamilyPacked { f2 fd, fs, ncl, ncdl, nfsl; float fdf, fsf, nclf, ncdlf, nfslf; };
+// shared-memory loads by 32-bit shared-window address (no generic->shared conversion in the hot loop)
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+// ordered after the phase-1 stores of the same warp (compiler barrier)
+__device__ __forceinline__ float4 lds128_ordered(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
 
-// one run of consecutive node pairs of uniform type T
-template <int T>
-__device__ __forceinline__ void quad_run(const NodePair* __restrict__ tab, int lo, int hi, const FamilyPacked& k,
-                                         f2& accY, f2& accUY) {
-#pragma unroll 1
-    for (int p = lo; p < hi; ++p) {
-        const NodePair n = tab[p * 32];
-        const f2 ad = mul2(k.fd, n.u), as = mul2(k.fs, n.v);
-        f2 y;
-        if (T == kMixed) {
-            // per-lane, per-half switch: both polynomials, selected
-            const f2 Ld = large2(ad), Ls = large2(as), Sd = small2(ad), Ss = small2(as);
-            float adl, adh, asl, ash, a0, a1, b0, b1;
-            upk(ad, adl, adh); upk(as, asl, ash);
-            const bool dl = adl <= kBesselSwitch, dh = adh <= kBesselSwitch;
-            const bool sl = asl <= kBesselSwitch, sh = ash <= kBesselSwitch;
-            upk(Ld, a0, a1); upk(Sd, b0, b1);
-            const f2 Vd = pk(dl ? b0 : a0, dh ? b1 : a1);
-            upk(Ls, a0, a1); upk(Ss, b0, b1);
-            const f2 Vs = pk(sl ? b0 : a0, sh ? b1 : a1);
-            const f2 kd = pk(dl ? k.ncdlf : k.nclf, dh ? k.ncdlf : k.nclf);
-            const f2 ks = pk(sl ? k.nfslf : 0.0f, sh ? k.nfslf : 0.0f);
-            const f2 e = fma2(ks, n.v, mul2(kd, n.u));
-            y = mul2(mul2(Vd, Vs), ex22(e));
-        } else {
-            const bool d_small = (T == kSS || T == kSL), s_small = (T == kSS || T == kLS);
-            const f2 Vd = d_small ? small2(ad) : large2(ad);
-            const f2 Vs = s_small ? small2(as) : large2(as);
-            f2 e = mul2(d_small ? k.ncdl : k.ncl, n.u);
-            if (s_small) e = fma2(k.nfsl, n.v, e);
-            y = mul2(mul2(Vd, Vs), ex22(e));
-        }
-        accY = add2(accY, y);
-        accUY = fma2(n.u, y, accUY);
+// One pass: W*64 node slots of a run of type T; lane l takes the adjacent node pairs at
+// ta, ta+512 B (nodes 2m, 2m+1).  W = 2 keeps four independent Horner chains in flight per
+// lane.  Slots outside the run -- the odd head slot and the tail of the run's last pass -- are
+// zeroed by a select on the ALU pipe, so the FMA pipe sees one straight-line FFMA2 body per
+// type.
+//   ta / tbb : shared addresses of this lane's first pair in the type's two table columns
+//   base     : 2*lane - head (wraps for the head slot), lenm = nvalid - head
+template <int T, int W>
+__device__ __forceinline__ void quad_pass(unsigned ta, unsigned tbb, unsigned base, unsigned lenm, const RunConsts& k,
+                                          f2& accY, f2& accUY) {
+    float4 a[W], b[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        a[w] = lds128(ta + 512 * w);
+        if (T == kLL || T == kLS) b[w] = lds128(tbb + 512 * w);
+        if (T == kSL) { const float2 h = lds64(tbb + 256 * w); b[w].x = h.x; b[w].y = h.y; }
     }
+    f2 pd[W], ps[W], e[W], u[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if (T == kLL) {
+            u[w] = pk(b[w].x, b[w].y);
+            pd[w] = mul2(dup(k.ifd), pk(a[w].x, a[w].y));
+            ps[w] = mul2(dup(k.ifs), pk(a[w].z, a[w].w));
+            e[w] = fma2(dup(k.k1L), u[w], pk(b[w].z, b[w].w));
+        } else if (T == kLS) {
+            u[w] = pk(b[w].x, b[w].y);
+            const f2 v = pk(a[w].z, a[w].w);
+            pd[w] = mul2(dup(k.ifd), pk(a[w].x, a[w].y));
+            ps[w] = mul2(dup(k.fs), v);
+            e[w] = fma2(dup(k.k2), v, fma2(dup(k.k1L), u[w], pk(b[w].z, b[w].w)));
+        } else if (T == kSL) {
+            u[w] = pk(b[w].x, b[w].y);
+            pd[w] = mul2(dup(k.fd), u[w]);
+            ps[w] = mul2(dup(k.ifs), pk(a[w].x, a[w].y));
+            e[w] = fma2(dup(k.k1S), u[w], pk(a[w].z, a[w].w));
+        } else {
+            u[w] = pk(a[w].x, a[w].y);
+            const f2 v = pk(a[w].z, a[w].w);
+            pd[w] = mul2(dup(k.fd), u[w]);
+            ps[w] = mul2(dup(k.fs), v);
+            e[w] = fma2(dup(k.k2), v, mul2(dup(k.k1S), u[w]));
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        pd[w] = (T == kLL || T == kLS) ? large2(pd[w]) : small2(pd[w]);
+        ps[w] = (T == kLL || T == kSL) ? large2(ps[w]) : small2(ps[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        float ylo, yhi;
+        upk(mul2(mul2(pd[w], ps[w]), ex22(e[w])), ylo, yhi);
+        ylo = (base + 64u * w < lenm) ? ylo : 0.0f;
+        yhi = (base + 64u * w + 1u < lenm) ? yhi : 0.0f;
+        const f2 y = pk(ylo, yhi);
+        acc_add2(accY, y);
+        acc_fma2(accUY, u[w], y);
+    }
+}
+
+// One run of uniform type T described by a run word (see run_word in so3_math.cuh); adds the
+// run's lane-partial sums of y and u*y, times the run's constant factor, to Y / UY.
+// tab: shared address of the QuadTables block + 16*lane (tab2: + 8*lane, the float2 column).
+template <int T>
+__device__ __forceinline__ void quad_run(unsigned tab, unsigned tab2, unsigned lane2, uint32_t word, float scale,
+                                         const RunConsts& k, float& Y, float& UY) {
+    constexpr unsigned offA = (T == kLL) ? offsetof(QuadTables, LLa) : (T == kLS) ? offsetof(QuadTables, LSa)
+                            : (T == kSL) ? offsetof(QuadTables, SLa) : offsetof(QuadTables, SSa);
+    constexpr unsigned offB = (T == kLL) ? offsetof(QuadTables, LLb) : (T == kLS) ? offsetof(QuadTables, LSb)
+                            : offsetof(QuadTables, SLb);
+    const unsigned m0 = word & 511u, head = (word >> 9) & 1u;
+    int slots = (int)((word >> 10) & 1023u);
+    unsigned ta = tab + offA + 16u * m0;
+    unsigned tbb = (T == kSL) ? tab2 + offB + 8u * m0 : tab + offB + 16u * m0;
+    unsigned base = lane2 - head;                    // slot of the lo half relative to the run start (wraps for the head slot)
+    const unsigned lenm = (unsigned)slots - head;
+    f2 accY = pk(0.f, 0.f), accUY = pk(0.f, 0.f);
+#pragma unroll 1
+    for (; slots > 64; slots -= 128, ta += 1024, tbb += (T == kSL) ? 512 : 1024, base += 128)
+        quad_pass<T, 2>(ta, tbb, base, lenm, k, accY, accUY);
+    if (slots > 0) quad_pass<T, 1>(ta, tbb, base, lenm, k, accY, accUY);
+    float lo, hi;
+    upk(accY, lo, hi); Y = fmaf(scale, lo + hi, Y);
+    upk(accUY, lo, hi); UY = fmaf(scale, lo + hi, UY);
 }
 
 __device__ __forceinline__ float warp_sum(float x) {
@@ -147,38 +231,49 @@ __device__ __forceinline__ float warp_sum(float x) {
     return x;
 }
 
+// trapezoid half weight of an end node, with the constant factor of the run it sits in
+__device__ __forceinline__ float end_node(const FamilyDesc& d, int i, const NodeVals& n) {
+    const int t = node_type(d, i);
+    return node_typed(d, t, n) * type_scale(d, t);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
 // K2: fused Fisher kernel
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 fisher_fused_kernel(FisherArgs p) {
-    __shared__ WarpScratch scratch[kWarpsPerBlock];
-    __shared__ NodePair node_tab[8 * 32];
-    __shared__ unsigned int hist_s[kHistBins1];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QuadTables& tb = *reinterpret_cast<QuadTables*>(smem_raw);
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw + sizeof(QuadTables));
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpScratch& ws = scratch[warp];
-    const bool want_hist = (p.hist != nullptr);
-    if (want_hist) {
-        for (int i = threadIdx.x; i < kHistBins1; i += kThreads) hist_s[i] = 0u;
-    }
-    // quadrature nodes of every (pair, lane): x rounded exactly like the reference
-    for (int i = threadIdx.x; i < 8 * 32; i += kThreads) {
-        const int pr = i >> 5, ln = i & 31;
-        const float x0 = quad_node((float)(64 * pr + ln)), x1 = quad_node((float)(64 * pr + 32 + ln));
-        node_tab[i].u = pk(add_rn(1.0f, -x0), add_rn(1.0f, -x1));
-        node_tab[i].v = pk(add_rn(1.0f, x0), add_rn(1.0f, x1));
+    // node tables (every block builds its own copy: 2 divides + 2 log2 per node, once)
+    for (int i = threadIdx.x; i < 2 * kTabPairs; i += kThreads) {
+        const NodeVals n = node_vals(i);
+        const int m = i >> 1, h = i & 1;
+        float* q;
+        q = reinterpret_cast<float*>(&tb.LLa[m]); q[h] = n.iu; q[2 + h] = n.iv;
+        q = reinterpret_cast<float*>(&tb.LLb[m]); q[h] = n.u;  q[2 + h] = n.Lu + n.Lv;
+        q = reinterpret_cast<float*>(&tb.LSa[m]); q[h] = n.iu; q[2 + h] = n.v;
+        q = reinterpret_cast<float*>(&tb.LSb[m]); q[h] = n.u;  q[2 + h] = n.Lu;
+        q = reinterpret_cast<float*>(&tb.SLa[m]); q[h] = n.iv; q[2 + h] = n.Lv;
+        q = reinterpret_cast<float*>(&tb.SLb[m]); q[h] = n.u;
+        q = reinterpret_cast<float*>(&tb.SSa[m]); q[h] = n.u;  q[2 + h] = n.v;
+        if (i == 0) tb.first = n;
+        if (i == kQuadNodes - 1) tb.last = n;
     }
     __syncthreads();
-    const NodePair* tab = node_tab + lane;
-    // trapezoid end points (weight 1/2): node 0 and node 511
-    float u_first, u_last, v_first, v_last, dummy;
-    upk(node_tab[0].u, u_first, dummy);       upk(node_tab[0].v, v_first, dummy);
-    upk(node_tab[7 * 32 + 31].u, dummy, u_last); upk(node_tab[7 * 32 + 31].v, dummy, v_last);
 
+    // shared-window addresses, laundered through asm so the hot loop keeps them in registers
+    // instead of re-deriving the window base (S2UR SR_CgaCtaId) at every use
+    unsigned tab_s = (unsigned)__cvta_generic_to_shared(&tb) + 16u * lane;          // float4 columns, this lane's pair
+    unsigned tab2_s = (unsigned)__cvta_generic_to_shared(&tb) + 8u * lane;          // float2 column
+    unsigned desc_s = (unsigned)__cvta_generic_to_shared(ws.desc);
+    asm volatile("" : "+r"(tab_s), "+r"(tab2_s), "+r"(desc_s));
     const long long warps_total = (long long)gridDim.x * kWarpsPerBlock;
     const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + warp;
     const int spw = p.samples_per_warp;
@@ -190,7 +285,7 @@ fisher_fused_kernel(FisherArgs p) {
         const int count = (int)min((long long)spw, p.n - base);
         const bool mine = lane < count;
 
-        // ---- phase 1: load + SVD (thread per sample) -------------------------
+        // ---- phase 1: load + SVD + run descriptors (thread per sample) ---------
         float s[3] = {0.f, 0.f, 0.f};
         float dot = 0.f;
         if (p.Sin) {
@@ -215,57 +310,56 @@ fisher_fused_kernel(FisherArgs p) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { ws.uv[k * 32 + lane] = U[k]; ws.uv[(9 + k) * 32 + lane] = V[k]; }
             }
-            __syncwarp();
         }
-        // per-sample run descriptors and trapezoid end-point corrections, still thread per sample
-        unsigned runs0, runs1, runs2;
+        // trapezoid end-point corrections (weight 1/2 at nodes 0 and 511) and the parked descriptors
         float cY0, cUY0, cN1, cN2;
         {
-            Family fam[3];
-            fisher_families(s, fam);
-            runs0 = family_runs(fam[0]); runs1 = family_runs(fam[1]); runs2 = family_runs(fam[2]);
-            const float f0 = fisher_node(fam[0], u_first, v_first), l0 = fisher_node(fam[0], u_last, v_last);
-            const float f1 = fisher_node(fam[1], u_first, v_first), l1 = fisher_node(fam[1], u_last, v_last);
-            const float f2v = fisher_node(fam[2], u_first, v_first), l2 = fisher_node(fam[2], u_last, v_last);
+            FamilyDesc fam[3];
+            fisher_families(s, reinterpret_cast<const float*>(tb.SSa), reinterpret_cast<const float*>(tb.SSa) + 2, p.cut_bits, fam);
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const FamilyDesc& d = fam[f];
+                uint32_t rw[3];
+                family_run_words(d, rw);
+                ws.desc[(f * 3 + 0) * 32 + lane] = make_float4(d.fd, d.fs, d.ifd, d.ifs);
+                ws.desc[(f * 3 + 1) * 32 + lane] = make_float4(d.k1L, d.k1S, d.scLS, d.scSL);
+                ws.desc[(f * 3 + 2) * 32 + lane] = make_float4(d.scMid, __uint_as_float(rw[0]), __uint_as_float(rw[1]), __uint_as_float(rw[2]));
+            }
+            const float uf = tb.first.u, ul = tb.last.u;
+            // (node 0 is only corrected where it was evaluated: a family with cut > 0 skipped it)
+            const float f0 = fam[0].cut ? 0.f : end_node(fam[0], 0, tb.first), l0 = end_node(fam[0], kQuadNodes - 1, tb.last);
+            const float f1 = fam[1].cut ? 0.f : end_node(fam[1], 0, tb.first), l1 = end_node(fam[1], kQuadNodes - 1, tb.last);
+            const float f2v = fam[2].cut ? 0.f : end_node(fam[2], 0, tb.first), l2 = end_node(fam[2], kQuadNodes - 1, tb.last);
             cY0 = 0.5f * (f0 + l0);
-            cUY0 = 0.5f * fmaf(u_first, f0, u_last * l0);
-            cN1 = 0.5f * ((f1 + l1) - fmaf(u_first, f1, u_last * l1));
-            cN2 = 0.5f * ((f2v + l2) - fmaf(u_first, f2v, u_last * l2));
+            cUY0 = 0.5f * fmaf(uf, f0, ul * l0);
+            cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1));
+            cN2 = 0.5f * ((f2v + l2) - fmaf(uf, f2v, ul * l2));
         }
+        __syncwarp();
 
         // ---- phase 2: quadrature (warp per sample) ---------------------------
         float Y0 = 1.f, UY0 = 0.f, N1 = 0.f, N2 = 0.f;
+        const unsigned lane2 = 2u * lane;
 #pragma unroll 1
         for (int j = 0; j < count; ++j) {
-            const float s0 = __shfl_sync(kFull, s[0], j);
-            const float s1 = __shfl_sync(kFull, s[1], j);
-            const float s2 = __shfl_sync(kFull, s[2], j);
-            const unsigned r0 = __shfl_sync(kFull, runs0, j);
-            const unsigned r1 = __shfl_sync(kFull, runs1, j);
-            const unsigned r2 = __shfl_sync(kFull, runs2, j);
             float pY0 = 0.f, pUY0 = 0.f, pN1 = 0.f, pN2 = 0.f;
 #pragma unroll 1
             for (int f = 0; f < 3; ++f) {
-                // family f: (lo, hi, c) as in fisher_families()
-                const float lo = (f == 2) ? s1 : s2;
-                const float hi = (f == 0) ? s1 : s0;
-                const float c = (f == 0) ? s0 + s2 : s1 + s2;
-                const unsigned runs = (f == 0) ? r0 : ((f == 1) ? r1 : r2);
-                const Family fm = make_family(lo, hi, c);
-                FamilyPacked k;
-                k.fd = dup(fm.fd); k.fs = dup(fm.fs); k.ncl = dup(fm.ncl); k.ncdl = dup(fm.ncdl); k.nfsl = dup(fm.nfsl);
-                k.fdf = fm.fd; k.fsf = fm.fs; k.nclf = fm.ncl; k.ncdlf = fm.ncdl; k.nfslf = fm.nfsl;
-                const int b1 = runs & 15, m0 = (runs >> 4) & 15, m1 = (runs >> 8) & 15, b4 = (runs >> 12) & 15;
-                f2 accY = pk(0.f, 0.f), accUY = pk(0.f, 0.f);
-                quad_run<kLS>(tab, 0, b1, k, accY, accUY);
-                quad_run<kMixed>(tab, b1, m0, k, accY, accUY);
-                if (runs & (1u << 16)) quad_run<kSS>(tab, m0, m1, k, accY, accUY);
-                else                   quad_run<kLL>(tab, m0, m1, k, accY, accUY);
-                quad_run<kMixed>(tab, m1, b4, k, accY, accUY);
-                quad_run<kSL>(tab, b4, 8, k, accY, accUY);
-                float ylo, yhi, ulo, uhi;
-                upk(accY, ylo, yhi); upk(accUY, ulo, uhi);
-                const float Y = ylo + yhi, UY = ulo + uhi;
+                const unsigned da = desc_s + 16u * (unsigned)(f * 96 + j);
+                const float4 d0 = lds128_ordered(da);
+                const float4 d1 = lds128_ordered(da + 512);
+                const float4 d2 = lds128_ordered(da + 1024);
+                RunConsts k;
+                k.fd = d0.x; k.fs = d0.y; k.ifd = d0.z; k.ifs = d0.w; k.k1L = d1.x; k.k1S = d1.y;
+                k.k2 = -(d0.y * kLog2e);
+                const uint32_t w0 = __float_as_uint(d2.y), w1 = __float_as_uint(d2.z), w2 = __float_as_uint(d2.w);
+                float Y = 0.f, UY = 0.f;
+                if (w0 & (1023u << 10)) quad_run<kLS>(tab_s, tab2_s, lane2, w0, d1.z, k, Y, UY);
+                if (w1 & (1023u << 10)) {
+                    if (w1 & (1u << 20)) quad_run<kLL>(tab_s, tab2_s, lane2, w1, d2.x, k, Y, UY);
+                    else                 quad_run<kSS>(tab_s, tab2_s, lane2, w1, d2.x, k, Y, UY);
+                }
+                if (w2 & (1023u << 10)) quad_run<kSL>(tab_s, tab2_s, lane2, w2, d1.w, k, Y, UY);
                 if (f == 0) { pY0 = Y; pUY0 = UY; }
                 else if (f == 1) pN1 = Y - UY;
                 else pN2 = Y - UY;
@@ -287,7 +381,6 @@ fisher_fused_kernel(FisherArgs p) {
             if (p.logC) p.logC[i] = st.logC;
             if (p.S) { p.S[3 * i] = s[0]; p.S[3 * i + 1] = s[1]; p.S[3 * i + 2] = s[2]; }
             if (p.G) { p.G[3 * i] = st.g[0]; p.G[3 * i + 1] = st.g[1]; p.G[3 * i + 2] = st.g[2]; }
-            if (want_hist) atomicAdd(&hist_s[entropy_key(st.entropy) >> kHistShift1], 1u);
             if (p.grad || p.Rout) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { U[k] = ws.uv[k * 32 + lane]; V[k] = ws.uv[(9 + k) * 32 + lane]; }
@@ -313,29 +406,32 @@ fisher_fused_kernel(FisherArgs p) {
     }
 
     if (bad && p.status) atomicOr(p.status, kStatusNonFinite);
-    if (want_hist) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < kHistBins1; i += kThreads) {
-            const unsigned int c = hist_s[i];
-            if (c) atomicAdd(p.hist + i, (unsigned long long)c);
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
 // K1: proper SVD only (batch_torch_A_to_R, analytical_mode, proper_svd)
 // thread per sample, tile of 128 records staged through shared memory
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+namespace {
+constexpr int kSvdWarps = 4;
+constexpr int kSvdThreads = kSvdWarps * 32;
+struct __align__(16) SvdScratch {
+    float a[kTileFloats];      // A in
+    float r[kTileFloats];      // rotation out
+    float uv[18 * 32];         // U,V [k][lane]
+};
+}  // namespace
+
+__global__ void __launch_bounds__(kSvdThreads)
 proper_svd_kernel(SvdArgs p) {
-    __shared__ WarpScratch scratch[kWarpsPerBlock];
+    __shared__ SvdScratch scratch[kSvdWarps];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    WarpScratch& ws = scratch[warp];
-    const long long warps_total = (long long)gridDim.x * kWarpsPerBlock;
+    SvdScratch& ws = scratch[warp];
+    const long long warps_total = (long long)gridDim.x * kSvdWarps;
     const long long tiles = (p.n + 31) / 32;
     bool bad = false;
-    for (long long tile = (long long)blockIdx.x * kWarpsPerBlock + warp; tile < tiles; tile += warps_total) {
+    for (long long tile = (long long)blockIdx.x * kSvdWarps + warp; tile < tiles; tile += warps_total) {
         const long long base = tile * 32;
         const int count = (int)min(32LL, p.n - base);
         load_tile(ws.a, p.A + base * 9, count, p.vec_ok, lane);
@@ -371,6 +467,111 @@ proper_svd_kernel(SvdArgs p) {
 }
 
 // ---------------------------------------------------------------------------
+// Body probe (bench/profiling aid): the W2 pass body of one run type in a tight loop, tables in
+// shared memory, no per-sample glue.  variant bits: 0-1 type, 2 skip LDS, 3 skip MUFU, 4 skip mask
+// ---------------------------------------------------------------------------
+template <int T, bool NO_LDS, bool NO_MUFU, bool NO_MASK>
+__device__ __forceinline__ void probe_pass(unsigned ta, unsigned tbb, unsigned base, unsigned lenm, const RunConsts& k,
+                                           f2& accY, f2& accUY, float4 ra, float4 rb) {
+    constexpr int W = 2;
+    float4 a[W], b[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if (NO_LDS) { a[w] = ra; b[w] = rb; }
+        else {
+            a[w] = lds128(ta + 512 * w);
+            if (T == kLL || T == kLS) b[w] = lds128(tbb + 512 * w);
+            if (T == kSL) { const float2 h = lds64(tbb + 256 * w); b[w].x = h.x; b[w].y = h.y; }
+        }
+    }
+    f2 pd[W], ps[W], e[W], u[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if (T == kLL) {
+            u[w] = pk(b[w].x, b[w].y);
+            pd[w] = mul2(dup(k.ifd), pk(a[w].x, a[w].y));
+            ps[w] = mul2(dup(k.ifs), pk(a[w].z, a[w].w));
+            e[w] = fma2(dup(k.k1L), u[w], pk(b[w].z, b[w].w));
+        } else {
+            u[w] = pk(a[w].x, a[w].y);
+            const f2 v = pk(a[w].z, a[w].w);
+            pd[w] = mul2(dup(k.fd), u[w]);
+            ps[w] = mul2(dup(k.fs), v);
+            e[w] = fma2(dup(k.k2), v, mul2(dup(k.k1S), u[w]));
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        pd[w] = (T == kLL) ? large2(pd[w]) : small2(pd[w]);
+        ps[w] = (T == kLL) ? large2(ps[w]) : small2(ps[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        float ylo, yhi;
+        upk(mul2(mul2(pd[w], ps[w]), NO_MUFU ? e[w] : ex22(e[w])), ylo, yhi);
+        if (!NO_MASK) {
+            ylo = (base + 64u * w < lenm) ? ylo : 0.0f;
+            yhi = (base + 64u * w + 1u < lenm) ? yhi : 0.0f;
+        }
+        const f2 y = pk(ylo, yhi);
+        acc_add2(accY, y);
+        acc_fma2(accUY, u[w], y);
+    }
+}
+
+template <int T, bool NO_LDS, bool NO_MUFU, bool NO_MASK>
+__global__ void __launch_bounds__(kThreads, 1) body_probe_kernel(float* sink, int iters, float seed) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QuadTables& tb = *reinterpret_cast<QuadTables*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 2 * kTabPairs; i += kThreads) {
+        const NodeVals n = node_vals(i);
+        const int m = i >> 1, h = i & 1;
+        float* q;
+        q = reinterpret_cast<float*>(&tb.LLa[m]); q[h] = n.iu; q[2 + h] = n.iv;
+        q = reinterpret_cast<float*>(&tb.LLb[m]); q[h] = n.u;  q[2 + h] = n.Lu + n.Lv;
+        q = reinterpret_cast<float*>(&tb.SSa[m]); q[h] = n.u;  q[2 + h] = n.v;
+    }
+    __syncthreads();
+    unsigned tab_s = (unsigned)__cvta_generic_to_shared(&tb) + 16u * lane;
+    asm volatile("" : "+r"(tab_s));
+    RunConsts k;
+    k.fd = seed; k.fs = seed * 0.5f; k.ifd = 1.0f / (seed * 40.f); k.ifs = 1.0f / (seed * 80.f); k.k1L = -seed; k.k1S = -seed * 1.5f; k.k2 = -0.7f * seed;
+    f2 accY = pk(0.f, 0.f), accUY = pk(0.f, 0.f);
+    const float4 ra = make_float4(1.5f * seed, 1.25f * seed, 1.1f * seed, 1.3f * seed), rb = make_float4(0.5f, 0.25f, -0.5f * seed, -0.7f);
+    const unsigned offA = (T == kLL) ? offsetof(QuadTables, LLa) : offsetof(QuadTables, SSa);
+    const unsigned offB = offsetof(QuadTables, LLb);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const unsigned o = ((unsigned)it & 1u) * 1024u + 64u * 16u;
+        probe_pass<T, NO_LDS, NO_MUFU, NO_MASK>(tab_s + offA + o, tab_s + offB + o, 2u * lane, 128u - ((unsigned)it & 3u), k, accY, accUY, ra, rb);
+    }
+    float a0, a1, b0, b1;
+    upk(accY, a0, a1); upk(accUY, b0, b1);
+    if (a0 + a1 + b0 + b1 == 123.456f) sink[0] = a0;
+}
+
+cudaError_t launch_body_probe(float* sink, int variant, int iters, int blocks, cudaStream_t stream) {
+    constexpr size_t kSmem = sizeof(QuadTables);
+#define SUHPE_BP(T, A, B, C) { cudaFuncSetAttribute(body_probe_kernel<T, A, B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem); \
+      body_probe_kernel<T, A, B, C><<<blocks, kThreads, kSmem, stream>>>(sink, iters, 1.0f); }
+    const int t = variant & 3;
+    const bool nl = variant & 4, nm = variant & 8, nk = variant & 16;
+    if (t == kLL) {
+        if (!nl && !nm && !nk) SUHPE_BP(kLL, false, false, false)
+        else if (nl && !nm && !nk) SUHPE_BP(kLL, true, false, false)
+        else if (!nl && nm && !nk) SUHPE_BP(kLL, false, true, false)
+        else if (!nl && !nm && nk) SUHPE_BP(kLL, false, false, true)
+        else SUHPE_BP(kLL, true, true, true)
+    } else {
+        if (!nl && !nm && !nk) SUHPE_BP(kSS, false, false, false)
+        else SUHPE_BP(kSS, true, true, true)
+    }
+#undef SUHPE_BP
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 static int sm_count() {
@@ -387,11 +588,12 @@ static int sm_count() {
 cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int sms = sm_count();
-    // resident warps the chip can hold for this kernel (occupancy-limited)
-    int blocks_per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fisher_fused_kernel, kThreads, 0);
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    const long long resident_warps = (long long)sms * blocks_per_sm * kWarpsPerBlock;
+    constexpr size_t kSmem = sizeof(QuadTables) + sizeof(WarpScratch) * kWarpsPerBlock;
+    static_assert(kSmem <= 227 * 1024, "fisher_fused_kernel shared memory exceeds one SM");
+    cudaError_t err = cudaFuncSetAttribute(fisher_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (err != cudaSuccess) return err;
+    // one persistent CTA of 20 warps per SM (the node tables are shared by the whole CTA)
+    const long long resident_warps = (long long)sms * kWarpsPerBlock;
     // small batches: spread samples over as many warps as possible (latency);
     // large batches: 32 samples per warp so the tile I/O is float4-coalesced
     long long spw = (p.n + resident_warps - 1) / resident_warps;
@@ -400,24 +602,26 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     p.samples_per_warp = (int)spw;
     const long long tiles = (p.n + spw - 1) / spw;
     long long blocks = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const long long max_blocks = (long long)sms * blocks_per_sm;
-    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks > sms) blocks = sms;
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     p.vec_ok = (spw == 32) && aligned(p.A) && aligned(p.Rgt) && aligned(p.grad) && aligned(p.Rout);
-    fisher_fused_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(p);
-    return cudaGetLastError();
+    fisher_fused_kernel<<<(unsigned)blocks, kThreads, kSmem, stream>>>(p);
+    err = cudaGetLastError();
+    // first radix-select pass over the entropies just written (they are still L2-resident)
+    if (err == cudaSuccess && p.hist) err = launch_select_hist_accumulate(p.entropy, p.n, p.hist, stream);
+    return err;
 }
 
 cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int sms = sm_count();
     const long long tiles = (p.n + 31) / 32;
-    long long blocks = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long blocks = (tiles + kSvdWarps - 1) / kSvdWarps;
     const long long max_blocks = (long long)sms * 8;
     if (blocks > max_blocks) blocks = max_blocks;
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     p.vec_ok = aligned(p.A) && aligned(p.R);
-    proper_svd_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+    proper_svd_kernel<<<(unsigned)blocks, kSvdThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,7 @@ struct FisherArgs {
     float* G;              // (n,3) d logC / d S                   | nullptr
     unsigned long long* hist;  // (2048) += histogram of the top 11 key bits of entropy | nullptr
     int* status;           // |= kStatus* | nullptr
+    int cut_bits;          // negligible-node cut: skipped mass < 2^-cut_bits of the normaliser sum; <= 0 = off
     int samples_per_warp;  // set by the launcher
     bool vec_ok;           // set by the launcher: float4 tile I/O allowed
 };
@@ -87,6 +88,8 @@ struct SelectState {
 
 cudaError_t launch_select_hist(const float* e, long long n, int pass, const SelectState* state,
                                unsigned long long* hist, cudaStream_t stream);
+// pass-1 histogram ADDED into hist (no clear): the "fused" first pass of K2's hist output
+cudaError_t launch_select_hist_accumulate(const float* e, long long n, unsigned long long* hist, cudaStream_t stream);
 // hist_parts: (parts, bins) gathered histograms, summed on the fly
 cudaError_t launch_select_scan(const unsigned long long* hist_parts, int parts, int pass,
                                SelectState* state, cudaStream_t stream);
@@ -95,6 +98,9 @@ cudaError_t launch_mask(const float* e, long long n, const float* thr_dev, float
                         uint8_t* mask, unsigned long long* kept, cudaStream_t stream);
 
 // FP32 pipe probe (roofline denominator measured on the box): returns FMA count executed
+// K2 pass-body probe (profiling aid): variant bits 0-1 run type, 2 no LDS, 3 no MUFU, 4 no mask;
+// passes executed = blocks * 16 warps * iters, 128 nodes each
+cudaError_t launch_body_probe(float* sink, int variant, int iters, int blocks, cudaStream_t stream);
 cudaError_t launch_fp32_probe(float* sink, int variant, int iters, int blocks, cudaStream_t stream);
 
 }  // namespace suhpe

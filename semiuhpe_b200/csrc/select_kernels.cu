@@ -217,6 +217,14 @@ cudaError_t launch_select_hist(const float* e, long long n, int pass, const Sele
     return cudaGetLastError();
 }
 
+cudaError_t launch_select_hist_accumulate(const float* e, long long n, unsigned long long* hist, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(e) & 15u) == 0;
+    const int blocks = stream_blocks((long long)kSelThreads * 4 * 4, n);
+    select_hist_kernel<<<blocks, kSelThreads, 0, stream>>>(e, n, 1, nullptr, hist, vec_ok);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_select_scan(const unsigned long long* hist_parts, int parts, int pass,
                                SelectState* state, cudaStream_t stream) {
     select_scan_kernel<<<1, 1024, 0, stream>>>(hist_parts, parts, pass, state);

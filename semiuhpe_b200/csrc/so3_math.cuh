@@ -291,77 +291,199 @@ SUHPE_HD float quad_node(float i_as_float) {
     return add_rn(mul_rn(i_as_float, (float)(2.0 / 511.0)), -1.0f);
 }
 
+// ----------------------------------------------------------------------------
+// Quadrature nodes and per-node constants.  x_i is rounded exactly like the
+// reference; u = 1-x, v = 1+x (both exact roundings the reference also performs,
+// and u + v == 2 holds exactly for all 512 nodes).  The reciprocal and the
+// half-log columns let the large-argument Bessel branch run without MUFU:
+//   P8(3.75/a)/sqrt(a), a = f*u  ==  P8'( (1/f)*(1/u) ) * rsqrt(f) * 2^(-1/2 log2 u)
+// 1/u comes from the table, 1/f and rsqrt(f) are per-sample constants, and the
+// node's 2^(-1/2 log2 u) is folded into the one exponential every node needs.
+// ----------------------------------------------------------------------------
+constexpr int kQuadNodes = 512;
+
+struct NodeVals { float u, v, iu, iv, Lu, Lv; };
+
+SUHPE_HD NodeVals node_vals(int i) {
+    NodeVals n;
+    if (i >= kQuadNodes) {            // padding behind the last node (results are discarded)
+        n.u = n.v = n.iu = n.iv = 1.0f; n.Lu = n.Lv = 0.0f;
+        return n;
+    }
+    const float x = quad_node((float)i);
+    n.u = add_rn(1.0f, -x);
+    n.v = add_rn(1.0f, x);
+    n.iu = div_rn(1.0f, n.u);         // +inf at node 511 (u == 0): that node is never large-d
+    n.iv = div_rn(1.0f, n.v);         // +inf at node 0   (v == 0): that node is never large-s
+    n.Lu = -0.5f * log2f(n.u);
+    n.Lv = -0.5f * log2f(n.v);
+    return n;
+}
+
+// ----------------------------------------------------------------------------
 // One family of the three Bessel-product integrands:
 //   y(x) = I0e(fd (1-x)) * I0e(fs (1+x)) * exp(c (x-1))
 // fam 0 (normaliser & d/ds1): fd=(s2-s3)/2 fs=(s2+s3)/2 c=s1+s3
 // fam 1 (d/ds2)             : fd=(s1-s3)/2 fs=(s1+s3)/2 c=s2+s3
 // fam 2 (d/ds3)             : fd=(s1-s2)/2 fs=(s1+s2)/2 c=s2+s3
 // (src/fisher/torch_norm_factor.py:33-63 with the cyclic shifts of :85-87).
-// The exponentials are evaluated as ex2(e) with e in the log2 domain, built from
-// per-family constants so that the scalar path below and the packed f32x2 loop
-// bodies of the kernel perform bit-identical operations:
-//   d large : kd = -c*log2e              d small : kd = -(c*log2e + fd*log2e)
-//   e = kd*u,  and if s small  e = fma(-fs*log2e, v, e)
-struct Family {
-    float fd, fs;        // |half difference|, |half sum|  (Bessel arguments are fd*u, fs*v)
-    float ncl, ncdl;     // -c*log2e, -(c*log2e + fd*log2e)
-    float nfsl;          // -fs*log2e
+//
+// a_d = fd*u falls and a_s = fs*v rises with the node index, so each Bessel factor
+// switches polynomial (at 3.75) at most once: nodes [0,id) are d-LARGE, [id,512)
+// d-small; nodes [0,js) are s-small, [js,512) s-LARGE.  With b0 = min(id,js) and
+// b1 = max(id,js) the 512 nodes split into three runs of uniform type
+//   [0,b0)  LS  (d large, s small)
+//   [b0,b1) LL if js < id, SS if id < js
+//   [b1,512) SL (d small, s large)
+// and inside a run every node executes the same instruction sequence:
+//   LL  y = P8(ifd*iu) P8(ifs*iv) 2^(k1L*u + Lu+Lv)                 * rsqrt(fd fs)
+//   LS  y = P8(ifd*iu) P6((fs*v)^2) 2^(k1L*u + Lu + k2*v)           * rsqrt(fd)
+//   SL  y = P6((fd*u)^2) P8(ifs*iv) 2^(k1S*u + Lv)                  * rsqrt(fs)
+//   SS  y = P6((fd*u)^2) P6((fs*v)^2) 2^(k1S*u + k2*v)
+// k1L = -c log2e, k1S = -(c+fd) log2e, k2 = -fs log2e: the exp(-a) of the small
+// branch (reference: poly/exp(|a|)) and exp(-c u) share ONE ex2 per node, and the
+// run's constant factor multiplies the run's partial sums once.
+// ----------------------------------------------------------------------------
+enum NodeType { kLS = 0, kLL = 1, kSS = 2, kSL = 3 };
+
+struct FamilyDesc {
+    float fd, fs, ifd, ifs;     // Bessel argument scales and their reciprocals
+    float k1L, k1S, k2;         // log2-domain exponent slopes
+    float scLS, scMid, scSL;    // constant factor of each run
+    int b0, b1;                 // run boundaries (node indices in [0,512])
+    int mid;                    // kLL or kSS
+    int cut;                    // nodes [0,cut) are provably negligible and skipped (0 = evaluate all)
 };
 
-SUHPE_HD Family make_family(float lo, float hi, float c) {
-    Family f;
-    f.fd = fabsf(0.5f * (hi - lo));
-    f.fs = fabsf(0.5f * (hi + lo));
+// P8 in r = 1/a (3.75^k folded into the coefficients): sqrt(a) * I0e(a) for a > 3.75
+SUHPE_HD float large_poly(float r) {
+    float p = kLg8;
+    p = fmaf(p, r, kLg7); p = fmaf(p, r, kLg6); p = fmaf(p, r, kLg5); p = fmaf(p, r, kLg4);
+    p = fmaf(p, r, kLg3); p = fmaf(p, r, kLg2); p = fmaf(p, r, kLg1); p = fmaf(p, r, kLg0);
+    return p;
+}
+
+// first node index whose argument f*t[i] is on the far side of the 3.75 switch.
+//   falling=true : t decreasing (u table); returns first i with f*t[i] <= 3.75
+//   falling=false: t increasing (v table); returns first i with f*t[i] >  3.75
+// The estimate from the node spacing is corrected against the exact fp32 products the
+// reference compares (src/fisher/torch_norm_factor.py:15-18), so the split is bit-faithful.
+// (the node columns are read from the kernel's pair-interleaved table: u at t4[4*(i/2) + i%2], v two floats on)
+SUHPE_HD float tab_at(const float* t4, int i) { return t4[((i >> 1) << 2) + (i & 1)]; }
+
+SUHPE_HD int switch_index(float f, const float* t, bool falling) {
+    const float q = div_rn(kBesselSwitch, f);                     // f = 0 -> +inf
+    const float est = falling ? (2.0f - q) * 255.5f : q * 255.5f;
+    int i = (int)fminf(fmaxf(ceilf(est), 0.0f), (float)kQuadNodes);   // NaN -> 0
+    if (falling) {
+        while (i > 0 && mul_rn(f, tab_at(t, i - 1)) <= kBesselSwitch) --i;
+        while (i < kQuadNodes && mul_rn(f, tab_at(t, i)) > kBesselSwitch) ++i;
+    } else {
+        while (i > 0 && mul_rn(f, tab_at(t, i - 1)) > kBesselSwitch) --i;
+        while (i < kQuadNodes && mul_rn(f, tab_at(t, i)) <= kBesselSwitch) ++i;
+    }
+    return i;
+}
+
+// Negligible-node cut.  Every factor I0e(.) is <= 1, so y_i <= exp(-c u_i) for each of the
+// three families, while the normaliser sum is at least its last term,
+//   F >= 1/2 y0(x=1) = 1/2 I0e(s2+s3) >= 0.195 / sqrt(max(s2+s3, 1)).
+// Nodes with  c u_i >= ln 512 + bits ln 2 + ln(sqrt(max(s2+s3,1)) / 0.195)  therefore add up
+// to less than 2^-bits F over a whole family: with bits = 26 that is a quarter of an fp32 ulp
+// of F, i.e. below what the reference's own fp32 torch.sum resolves.  u falls with the node
+// index, so those nodes are a prefix [0,cut).  bits <= 0 disables the cut.
+SUHPE_HD float cut_threshold(const float* s, int bits) {
+    if (bits <= 0) return INFINITY;
+    const float m = fmaxf(s[1] + s[2], 1.0f);
+    return 6.2383246f + 0.69314718f * (float)bits + logf(sqrt_rn(m) * (1.0f / 0.195f)) + 0.01f;
+}
+SUHPE_HD int cut_index(float c, float thr) {
+    // first node that must be kept: u_i < thr / c  <=>  i > (2 - thr/c) * 255.5 ; one node of slack
+    const float lim = (2.0f - div_rn(thr, c)) * 255.5f - 1.0f;        // c <= 0 or thr = inf -> -inf/NaN -> 0
+    return (int)fminf(fmaxf(floorf(lim), 0.0f), (float)(kQuadNodes - 1));
+}
+
+// (lo, hi, c) -> descriptor;  utab/vtab: the 512 node values u_i, v_i in the interleaved layout of tab_at()
+SUHPE_HD FamilyDesc make_family(float lo, float hi, float c, const float* utab, const float* vtab, float cut_thr) {
+    FamilyDesc d;
+    d.fd = fabsf(0.5f * (hi - lo));
+    d.fs = fabsf(0.5f * (hi + lo));
+    d.ifd = div_rn(1.0f, d.fd);
+    d.ifs = div_rn(1.0f, d.fs);
     const float cl = c * kLog2e;
-    f.ncl = -cl;
-    f.ncdl = -(cl + f.fd * kLog2e);
-    f.nfsl = -(f.fs * kLog2e);
-    return f;
+    d.k1L = -cl;
+    d.k1S = -(cl + d.fd * kLog2e);
+    d.k2 = -(d.fs * kLog2e);
+    const int id = switch_index(d.fd, utab, true);
+    const int js = switch_index(d.fs, vtab, false);
+    d.b0 = id < js ? id : js;
+    d.b1 = id < js ? js : id;
+    d.mid = (js < id) ? kLL : kSS;
+    d.scLS = div_rn(1.0f, sqrt_rn(d.fd));
+    d.scSL = div_rn(1.0f, sqrt_rn(d.fs));
+    d.scMid = (d.mid == kLL) ? d.scLS * d.scSL : 1.0f;
+    d.cut = cut_index(c, cut_thr);
+    return d;
 }
 
-SUHPE_HD void fisher_families(const float* s, Family* f) {
-    f[0] = make_family(s[2], s[1], s[0] + s[2]);
-    f[1] = make_family(s[2], s[0], s[1] + s[2]);
-    f[2] = make_family(s[1], s[0], s[1] + s[2]);
+SUHPE_HD void fisher_families(const float* s, const float* utab, const float* vtab, int cut_bits, FamilyDesc* f) {
+    const float thr = cut_threshold(s, cut_bits);
+    f[0] = make_family(s[2], s[1], s[0] + s[2], utab, vtab, thr);
+    f[1] = make_family(s[2], s[0], s[1] + s[2], utab, vtab, thr);
+    f[2] = make_family(s[1], s[0], s[1] + s[2], utab, vtab, thr);
 }
 
-// Scalar node evaluation, any mix of branches (generic lanes of the kernel, the
-// trapezoid end-point corrections and the host emulation).  u = 1-x, v = 1+x.
-SUHPE_HD float fisher_node(const Family& f, float u, float v) {
-    const float ad = f.fd * u;
-    const float as = f.fs * v;
-    const bool sd = ad <= kBesselSwitch, ss = as <= kBesselSwitch;
-    const float pd = sd ? i0_small_poly(ad) : i0e_large(ad);
-    const float ps = ss ? i0_small_poly(as) : i0e_large(as);
-    float e = (sd ? f.ncdl : f.ncl) * u;
-    e = fmaf(ss ? f.nfsl : 0.0f, v, e);
+// ----------------------------------------------------------------------------
+// Run words.  The thread that owns a sample packs each of the (up to) three runs of a family
+// into one word, so the warp that replays the quadrature does no boundary arithmetic:
+//   bits 0-8  m0: first node pair of the run (start >> 1)
+//   bit  9    head: the run starts at the odd node of that pair (slot 0 of the first pass is masked)
+//   bits 10-19 slots: end - 2*m0, the number of node slots from the pair's first node to the run's
+//             end (0 = empty run); passes of 128 slots while more than 64 remain, then one of 64
+//   bit  20   the middle run is LL (else SS)
+// ----------------------------------------------------------------------------
+SUHPE_HD uint32_t run_word(int lo, int end, int cut, bool mid_ll) {
+    const int start = lo > cut ? lo : cut;
+    if (end <= start) return mid_ll ? (1u << 20) : 0u;
+    const int m0 = start >> 1;
+    return (uint32_t)m0 | ((uint32_t)(start & 1) << 9) | ((uint32_t)(end - 2 * m0) << 10) | (mid_ll ? (1u << 20) : 0u);
+}
+SUHPE_HD void family_run_words(const FamilyDesc& d, uint32_t* w) {
+    w[0] = run_word(0, d.b0, d.cut, false);
+    w[1] = run_word(d.b0, d.b1, d.cut, d.mid == kLL);
+    w[2] = run_word(d.b1, kQuadNodes, d.cut, false);
+}
+
+SUHPE_HD int node_type(const FamilyDesc& d, int i) {
+    return i < d.b0 ? kLS : (i < d.b1 ? d.mid : kSL);
+}
+SUHPE_HD float type_scale(const FamilyDesc& d, int type) {
+    return type == kLS ? d.scLS : (type == kSL ? d.scSL : (type == kLL ? d.scLS * d.scSL : 1.0f));
+}
+
+// Scalar node evaluation WITHOUT the run's constant factor: the same operations, in the
+// same order, as the packed f32x2 run bodies of the kernel (trapezoid end-point
+// corrections and the host emulation use this).
+SUHPE_HD float node_typed(const FamilyDesc& d, int type, const NodeVals& n) {
+    float pd, ps, e;
+    if (type == kLL) {
+        pd = large_poly(d.ifd * n.iu);
+        ps = large_poly(d.ifs * n.iv);
+        e = fmaf(d.k1L, n.u, n.Lu + n.Lv);
+    } else if (type == kLS) {
+        pd = large_poly(d.ifd * n.iu);
+        ps = i0_small_poly(d.fs * n.v);
+        e = fmaf(d.k2, n.v, fmaf(d.k1L, n.u, n.Lu));
+    } else if (type == kSL) {
+        pd = i0_small_poly(d.fd * n.u);
+        ps = large_poly(d.ifs * n.iv);
+        e = fmaf(d.k1S, n.u, n.Lv);
+    } else {
+        pd = i0_small_poly(d.fd * n.u);
+        ps = i0_small_poly(d.fs * n.v);
+        e = fmaf(d.k2, n.v, d.k1S * n.u);
+    }
     return (pd * ps) * mufu_ex2(e);
-}
-
-// Run descriptor of one family over the 8 node pairs-of-iterations (64 nodes each):
-// pairs [0,b1) are (d large, s small); [b1,m0) mixed; [m0,m1) uniform middle run
-// (both small if mid_ss else both large); [m1,b4) mixed; [b4,8) (d small, s large).
-// Classification is conservative by one node; mixed pairs are evaluated per lane,
-// so the result does not depend on it.  Packed as b1 | m0<<4 | m1<<8 | b4<<12 | mid_ss<<16.
-SUHPE_HD unsigned family_runs(const Family& f) {
-    const float nodes_per_unit = 255.5f;              // 511/2 nodes per unit of x
-    // nodes with index < id are large for d (a_d = fd*u, u ~ 2 - i*h decreasing);
-    // nodes with index <= is are small for s (a_s = fs*v, v ~ i*h increasing)
-    const float id = (2.0f - kBesselSwitch / f.fd) * nodes_per_unit;   // fd = 0 -> -inf
-    const float is = (kBesselSwitch / f.fs) * nodes_per_unit;          // fs = 0 -> +inf
-    const float inv64 = 1.0f / 64.0f;
-    const float dLf = fminf(fmaxf(floorf(id * inv64), 0.0f), 8.0f);
-    const float dSf = fminf(fmaxf(ceilf((id + 1.0f) * inv64), 0.0f), 8.0f);
-    const float sSf = fminf(fmaxf(floorf(is * inv64), 0.0f), 8.0f);
-    const float sLf = fminf(fmaxf(ceilf((is + 1.0f) * inv64), 0.0f), 8.0f);
-    const int dL = (int)dLf, dS = (int)dSf, sS = (int)sSf, sL = (int)sLf;
-    const int b1 = dL < sS ? dL : sS;
-    const int b4 = dS > sL ? dS : sL;
-    const bool mid_ss = dL <= sS;
-    int m0 = mid_ss ? dS : sL;
-    int m1 = mid_ss ? sS : dL;
-    if (m0 >= m1) { m0 = b1; m1 = b1; }
-    return (unsigned)b1 | ((unsigned)m0 << 4) | ((unsigned)m1 << 8) | ((unsigned)b4 << 12) | (mid_ss ? 1u << 16 : 0u);
 }
 
 // Closing arithmetic once the four trapezoid sums are known.

@@ -20,10 +20,11 @@ void emul_proper_svd(const float* A, long n, float* R, float* S, float* U, float
 
 }  // extern "C"
 
-// Mirrors the warp decomposition of the kernel: lane l owns, in pair p of 8, the nodes
-// 64p+l (lo half) and 64p+32+l (hi half); per family it keeps packed sums of y and u*y,
-// adds the halves, and the warp butterfly-reduces {Y0, UY0, N1, N2}.  The trapezoid
-// end-point halves are subtracted afterwards.
+// Mirrors the warp decomposition of the kernel: per family the 512 nodes split into up to
+// three runs of uniform type; a run is walked in passes of 64 nodes, lane l taking the adjacent
+// pair (2m, 2m+1), slots outside [start,end) zeroed; each lane keeps (lo,hi) partial sums of y
+// and u*y per run, scales them by the run's constant factor, and the warp butterfly-reduces
+// {Y0, UY0, N1, N2}.  The trapezoid end-point halves are subtracted afterwards.
 static float butterfly(float* v) {
     for (int off = 16; off >= 1; off >>= 1)
         for (int lane = 0; lane < 32; ++lane)
@@ -31,35 +32,75 @@ static float butterfly(float* v) {
     return v[0];
 }
 
-static void quadrature(const float* s, float* F, float* N0, float* N1, float* N2) {
-    Family fam[3];
-    fisher_families(s, fam);
+struct Tables {
+    NodeVals n[576];
+    float uv[1024 + 2];      // pair-interleaved (u0,u1,v0,v1) like the kernel's SSa column; v = u + 2
+    const float* u;
+    const float* v;
+    Tables() {
+        for (int i = 0; i < 576; ++i) n[i] = node_vals(i);
+        for (int i = 0; i < 512; ++i) { uv[((i >> 1) << 2) + (i & 1)] = n[i].u; uv[((i >> 1) << 2) + 2 + (i & 1)] = n[i].v; }
+        u = uv; v = uv + 2;
+    }
+};
+static const Tables& tables() { static Tables t; return t; }
+
+// one run for one lane, walked exactly like quad_run/quad_pass: passes of 128 slots while more than
+// 64 remain, then one of 64; slot masks from (base, lenm); the run's factor applied at the end
+static void run_lane(const FamilyDesc& d, int type, uint32_t word, int lane, float* Y, float* UY) {
+    const Tables& tb = tables();
+    const unsigned m0 = word & 511u, head = (word >> 9) & 1u;
+    int slots = (int)((word >> 10) & 1023u);
+    if (slots == 0) return;
+    const unsigned lenm = (unsigned)slots - head;
+    unsigned base = 2u * lane - head, m = m0;
+    float ylo = 0, yhi = 0, ulo = 0, uhi = 0;
+    while (slots > 0) {
+        const int W = slots > 64 ? 2 : 1;
+        for (int w = 0; w < W; ++w) {
+            const int i0 = 2 * (int)(m + lane + 32 * w), i1 = i0 + 1;
+            float y0 = node_typed(d, type, tb.n[i0]), y1 = node_typed(d, type, tb.n[i1]);
+            if (!(base + 64u * w < lenm)) y0 = 0.f;
+            if (!(base + 64u * w + 1u < lenm)) y1 = 0.f;
+            ylo += y0; yhi += y1;
+            ulo = fmaf(tb.n[i0].u, y0, ulo); uhi = fmaf(tb.n[i1].u, y1, uhi);
+        }
+        slots -= 64 * W; m += 32 * W; base += 64 * W;
+    }
+    const float sc = type_scale(d, type);
+    *Y = fmaf(sc, ylo + yhi, *Y);
+    *UY = fmaf(sc, ulo + uhi, *UY);
+}
+
+static float end_node(const FamilyDesc& d, int i) {
+    const int t = node_type(d, i);
+    return node_typed(d, t, tables().n[i]) * type_scale(d, t);
+}
+
+static void quadrature(const float* s, int cut_bits, float* F, float* N0, float* N1, float* N2) {
+    const Tables& tb = tables();
+    FamilyDesc fam[3];
+    fisher_families(s, tb.u, tb.v, cut_bits, fam);
     float pY0[32], pUY0[32], pN1[32], pN2[32];
-    float x_nodes[512];
-    for (int i = 0; i < 512; ++i) x_nodes[i] = quad_node((float)i);
     for (int lane = 0; lane < 32; ++lane) {
         for (int f = 0; f < 3; ++f) {
-            float ylo = 0, yhi = 0, ulo = 0, uhi = 0;
-            for (int p = 0; p < 8; ++p) {
-                const float x0 = x_nodes[64 * p + lane], x1 = x_nodes[64 * p + 32 + lane];
-                const float u0 = add_rn(1.0f, -x0), v0 = add_rn(1.0f, x0);
-                const float u1 = add_rn(1.0f, -x1), v1 = add_rn(1.0f, x1);
-                const float y0 = fisher_node(fam[f], u0, v0), y1 = fisher_node(fam[f], u1, v1);
-                ylo += y0; yhi += y1;
-                ulo = fmaf(u0, y0, ulo); uhi = fmaf(u1, y1, uhi);
-            }
-            const float Y = ylo + yhi, UY = ulo + uhi;
+            const FamilyDesc& d = fam[f];
+            uint32_t w[3];
+            family_run_words(d, w);
+            float Y = 0, UY = 0;
+            run_lane(d, kLS, w[0], lane, &Y, &UY);
+            run_lane(d, (w[1] >> 20) & 1 ? kLL : kSS, w[1], lane, &Y, &UY);
+            run_lane(d, kSL, w[2], lane, &Y, &UY);
             if (f == 0) { pY0[lane] = Y; pUY0[lane] = UY; }
             else if (f == 1) pN1[lane] = Y - UY;
             else pN2[lane] = Y - UY;
         }
     }
     const float Y0 = butterfly(pY0), UY0 = butterfly(pUY0), n1 = butterfly(pN1), n2 = butterfly(pN2);
-    const float uf = add_rn(1.0f, -x_nodes[0]), vf = add_rn(1.0f, x_nodes[0]);
-    const float ul = add_rn(1.0f, -x_nodes[511]), vl = add_rn(1.0f, x_nodes[511]);
-    const float f0 = fisher_node(fam[0], uf, vf), l0 = fisher_node(fam[0], ul, vl);
-    const float f1 = fisher_node(fam[1], uf, vf), l1 = fisher_node(fam[1], ul, vl);
-    const float f2 = fisher_node(fam[2], uf, vf), l2 = fisher_node(fam[2], ul, vl);
+    const float uf = tb.n[0].u, ul = tb.n[511].u;
+    const float f0 = fam[0].cut ? 0.f : end_node(fam[0], 0), l0 = end_node(fam[0], 511);
+    const float f1 = fam[1].cut ? 0.f : end_node(fam[1], 0), l1 = end_node(fam[1], 511);
+    const float f2 = fam[2].cut ? 0.f : end_node(fam[2], 0), l2 = end_node(fam[2], 511);
     const float cY0 = 0.5f * (f0 + l0);
     const float cUY0 = 0.5f * fmaf(uf, f0, ul * l0);
     const float cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1));
@@ -70,30 +111,59 @@ static void quadrature(const float* s, float* F, float* N0, float* N1, float* N2
     *N2 = n2 - cN2;
 }
 
-// run descriptors must classify conservatively: every pair marked uniform really is
-extern "C" int emul_check_runs(const float* S, long n) {
-    float x_nodes[512];
-    for (int i = 0; i < 512; ++i) x_nodes[i] = quad_node((float)i);
+// every node of [cut,512) must be covered exactly once by the passes the run words describe, with the
+// run type the reference's branch choice dictates, and no pass may reach past the padded tables
+extern "C" int emul_check_items(const float* S, long n, int cut_bits) {
+    const Tables& tb = tables();
     int bad = 0;
     for (long i = 0; i < n; ++i) {
-        Family fam[3];
-        fisher_families(S + 3 * i, fam);
+        FamilyDesc fam[3];
+        fisher_families(S + 3 * i, tb.u, tb.v, cut_bits, fam);
         for (int f = 0; f < 3; ++f) {
-            const unsigned r = family_runs(fam[f]);
-            const int b1 = r & 15, m0 = (r >> 4) & 15, m1 = (r >> 8) & 15, b4 = (r >> 12) & 15;
-            const bool mid_ss = (r >> 16) & 1;
-            if (!(0 <= b1 && b1 <= m0 && m0 <= m1 && m1 <= b4 && b4 <= 8)) { ++bad; continue; }
-            for (int p = 0; p < 8; ++p) {
-                int want_d, want_s;   // 0 large, 1 small, -1 any
-                if (p < b1) { want_d = 0; want_s = 1; }
-                else if (p >= b4) { want_d = 1; want_s = 0; }
-                else if (p >= m0 && p < m1) { want_d = want_s = mid_ss ? 1 : 0; }
-                else continue;
-                for (int k = 64 * p; k < 64 * p + 64; ++k) {
-                    const float u = add_rn(1.0f, -x_nodes[k]), v = add_rn(1.0f, x_nodes[k]);
-                    const int sd = fam[f].fd * u <= kBesselSwitch, ss = fam[f].fs * v <= kBesselSwitch;
-                    if (sd != want_d || ss != want_s) ++bad;
+            uint32_t w[3];
+            family_run_words(fam[f], w);
+            int seen[512] = {};
+            for (int r = 0; r < 3; ++r) {
+                const int type = r == 0 ? kLS : (r == 2 ? kSL : ((w[r] >> 20) & 1 ? kLL : kSS));
+                const unsigned m0 = w[r] & 511u, head = (w[r] >> 9) & 1u;
+                int slots = (int)((w[r] >> 10) & 1023u);
+                if (slots == 0) continue;
+                unsigned m = m0;
+                int done = 0;
+                while (slots - done > 0) {
+                    const int W = (slots - done) > 64 ? 2 : 1;
+                    if (m + 32u * W > 288u) ++bad;
+                    m += 32 * W; done += 64 * W;
                 }
+                for (int t = (int)head; t < slots; ++t) {
+                    const int node = 2 * (int)m0 + t;
+                    if (node >= 512 || node < fam[f].cut) { ++bad; continue; }
+                    ++seen[node];
+                    if (node_type(fam[f], node) != type) ++bad;
+                }
+            }
+            for (int node = 0; node < 512; ++node)
+                if (seen[node] != (node >= fam[f].cut ? 1 : 0)) ++bad;
+        }
+    }
+    return bad;
+}
+
+// the run boundaries must reproduce the reference's per-node branch choice exactly:
+// node i is d-small iff fl(fd*u_i) <= 3.75 and s-small iff fl(fs*v_i) <= 3.75
+extern "C" int emul_check_runs(const float* S, long n) {
+    const Tables& tb = tables();
+    int bad = 0;
+    for (long i = 0; i < n; ++i) {
+        FamilyDesc fam[3];
+        fisher_families(S + 3 * i, tb.u, tb.v, 0, fam);
+        for (int f = 0; f < 3; ++f) {
+            const FamilyDesc& d = fam[f];
+            if (!(0 <= d.b0 && d.b0 <= d.b1 && d.b1 <= 512)) { ++bad; continue; }
+            for (int k = 0; k < 512; ++k) {
+                const bool sd = d.fd * tb.n[k].u <= kBesselSwitch, ss = d.fs * tb.n[k].v <= kBesselSwitch;
+                const int want = sd ? (ss ? kSS : kSL) : (ss ? kLS : kLL);
+                if (node_type(d, k) != want) ++bad;
             }
         }
     }
@@ -101,14 +171,14 @@ extern "C" int emul_check_runs(const float* S, long n) {
 }
 
 extern "C" {
-void emul_fisher(const float* A, const float* Rgt, long n, float overreg,
+void emul_fisher(const float* A, const float* Rgt, long n, float overreg, int cut_bits,
                  float* nll, float* grad, float* Rout, float* entropy, float* logC, float* S, float* G) {
     for (long i = 0; i < n; ++i) {
         const float* a = A + 9 * i;
         float u[9], v[9], s[3];
         proper_svd3(a, u, v, s);
         float F, N0, N1, N2;
-        quadrature(s, &F, &N0, &N1, &N2);
+        quadrature(s, cut_bits, &F, &N0, &N1, &N2);
         FisherStats st = fisher_finish(s, F, N0, N1, N2);
         u_diag_vt(u, v, 1.f, 1.f, 1.f, Rout + 9 * i);
         float gm[9];

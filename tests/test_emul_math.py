@@ -21,12 +21,12 @@ def emul(built):
     return ctypes.CDLL(os.path.join(HERE, "emul", "libemul.so"))
 
 
-def run_fisher(emul, A, R, overreg):
+def run_fisher(emul, A, R, overreg, cut_bits=26):
     A = np.ascontiguousarray(A.reshape(-1, 9), np.float32)
     R = np.ascontiguousarray(R.reshape(-1, 9), np.float32)
     n = len(A)
     o = {k: np.zeros(s, np.float32) for k, s in dict(nll=n, grad=(n, 9), rot=(n, 9), ent=n, logC=n, S=(n, 3), G=(n, 3)).items()}
-    emul.emul_fisher(P(A), P(R), ctypes.c_long(n), ctypes.c_float(overreg), P(o["nll"]), P(o["grad"]), P(o["rot"]),
+    emul.emul_fisher(P(A), P(R), ctypes.c_long(n), ctypes.c_float(overreg), ctypes.c_int(cut_bits), P(o["nll"]), P(o["grad"]), P(o["rot"]),
                      P(o["ent"]), P(o["logC"]), P(o["S"]), P(o["G"]))
     return o
 
@@ -72,6 +72,25 @@ def test_fisher_against_golden(emul, golden):
     assert o["nll"][zero] == 0 and o["ent"][zero] == 0
     np.testing.assert_array_equal(o["rot"][zero], np.eye(3, dtype=np.float32).ravel())
     np.testing.assert_allclose(o["grad"][zero], -np.eye(3).ravel(), atol=1e-6)
+
+
+def test_negligible_node_cut_is_below_rounding(emul, golden):
+    """Skipping the provably negligible node prefix (cut_bits=26, the default) must not move any
+    output by more than fp32 rounding of the full 512-node evaluation (cut_bits=0)."""
+    g = golden("fisher")
+    full = run_fisher(emul, g["A"], g["R"], float(g["overreg"]), cut_bits=0)
+    cut = run_fisher(emul, g["A"], g["R"], float(g["overreg"]), cut_bits=26)
+    assert_close(cut["logC"], full["logC"], 2e-7, 2e-7, "logC")
+    assert_close(cut["nll"], full["nll"], 2e-7, 1e-6, "nll")
+    assert np.abs(cut["G"] - full["G"]).max() < 6e-7
+    # entropy = log f + sum_j s_j (1 - g_j) amplifies the few-ulp regrouping noise of g by |s|
+    assert (np.abs(cut["ent"] - full["ent"]) <= 2e-6 + 6e-7 * np.abs(full["S"]).sum(1)).all()
+    rng = np.random.default_rng(5)
+    A = (rng.standard_normal((4000, 9)) * rng.choice([0.1, 1, 5, 10, 30, 100], (4000, 1))).astype(np.float32)
+    R = np.tile(np.eye(3, dtype=np.float32).ravel(), (4000, 1))
+    full, cut = run_fisher(emul, A, R, 1.025, 0), run_fisher(emul, A, R, 1.025, 26)
+    assert np.abs(cut["G"] - full["G"]).max() < 6e-7
+    assert_close(cut["logC"], full["logC"], 2e-7, 2e-7, "logC random")
 
 
 def test_svd_properties(emul):
@@ -135,9 +154,10 @@ def test_metrics_against_golden(emul, golden):
             np.testing.assert_allclose(frob, g["frob_full"], rtol=1e-5, atol=1e-6)
 
 
-def test_run_descriptors_are_conservative(emul):
-    """Every node pair the kernel treats as branch-uniform really is (all 64 nodes on the
-    declared side of the 3.75 switch), for singular values from 0 to 1e6."""
+def test_run_boundaries_are_exact(emul):
+    """The three uniform-type runs the kernel derives per family reproduce the reference's
+    per-node choice of Bessel polynomial (|a| <= 3.75 on the fp32 product) for every one of
+    the 512 nodes, for singular values from 0 to 1e6."""
     rng = np.random.default_rng(1)
     S = np.abs(rng.standard_normal((200000, 3))).astype(np.float32) * (10.0 ** rng.uniform(-3, 3, (200000, 1))).astype(np.float32)
     S = -np.sort(-S, axis=1)
@@ -147,3 +167,6 @@ def test_run_descriptors_are_conservative(emul):
     S[100:150] = np.float32(3.75) * np.array([1.0, 1.0, 1.0], np.float32)
     S = np.ascontiguousarray(S, np.float32)
     assert emul.emul_check_runs(P(S), ctypes.c_long(len(S))) == 0
+    # the flat pass-item list the warp replays covers every kept node exactly once, with the right type
+    for bits in (0, 26):
+        assert emul.emul_check_items(P(S[:60000]), ctypes.c_long(60000), ctypes.c_int(bits)) == 0

@@ -182,3 +182,36 @@ def test_full_size_properties(cuda):
     assert_close(o1["nll"][idx.to(cuda)].cpu().numpy(), ref.detach().numpy(), RTOL, ATOL, "nll sample")
     assert grad_rel_err(o1["grad"][idx.to(cuda)].cpu().numpy(), leaf.grad.numpy()).max() < 1e-4
     assert_close(o1["entropy"][idx.to(cuda)].cpu().numpy(), orc.fisher_entropy(sub_A).numpy(), RTOL, ATOL, "entropy sample")
+
+
+def test_negligible_node_cut_on_off(cuda, golden):
+    """K2 skips the provably negligible node prefix by default (suhpe_set_quadrature_cut_bits, 26);
+    evaluating all 512 nodes (bits=0) must give the same numbers to fp32 rounding, and both
+    settings must hold the golden parity."""
+    import semiuhpe_b200
+    from semiuhpe_b200 import _ops
+    g = golden("fisher")
+    A = torch.from_numpy(g["A"]).to(cuda).reshape(-1, 9)
+    R = torch.from_numpy(g["R"]).to(cuda)
+    regime = np.isin(g["names"], ["generic1", "generic10", "generic30", "realistic", "neardegenerate"])
+    gen = torch.Generator().manual_seed(11)
+    scales = torch.tensor([0.1, 1.0, 5.0, 10.0, 30.0, 100.0])[torch.randint(0, 6, (20000, 1), generator=gen)]
+    Ar = (torch.randn(20000, 9, generator=gen) * scales).to(cuda)
+    Rr = random_rotations(20000, gen).to(cuda)
+    outs = {}
+    prev = semiuhpe_b200.set_quadrature_cut_bits(0)
+    try:
+        for bits in (0, 26):
+            semiuhpe_b200.set_quadrature_cut_bits(bits)
+            o = _ops.fisher_fused(A, R, float(g["overreg"]), nll=True, entropy=True, grad=True)
+            assert_close(o["nll"].cpu().numpy()[regime], g["nll"][regime], RTOL, ATOL, f"nll bits={bits}")
+            assert_close(o["entropy"].cpu().numpy()[regime], g["entropy"][regime], RTOL, ATOL, f"entropy bits={bits}")
+            outs[bits] = _ops.fisher_fused(Ar, Rr, 1.025, nll=True, entropy=True, grad=True, logC=True, G=True, S=True)
+    finally:
+        semiuhpe_b200.set_quadrature_cut_bits(prev)
+    full, cut = outs[0], outs[26]
+    assert_close(cut["logC"].cpu().numpy(), full["logC"].cpu().numpy(), 3e-7, 3e-7, "logC")
+    assert (cut["G"] - full["G"]).abs().max().item() < 6e-7
+    S1 = full["S"].abs().sum(1)
+    assert bool(((cut["entropy"] - full["entropy"]).abs() <= 2e-6 + 6e-7 * S1).all())
+    assert grad_rel_err(cut["grad"].cpu().numpy(), full["grad"].cpu().numpy()).max() < 2e-6
