@@ -88,53 +88,69 @@ SUHPE_HD float sqrt_rn(float a) {
 // the third left vector.  No division by the smallest singular value anywhere,
 // so rank-deficient input (A = 0 gives U = V = R = I like LAPACK) is safe.
 // ----------------------------------------------------------------------------
-constexpr int kJacobiSweeps = 5;
+constexpr int kJacobiSweeps = 5;          // fp32: converged to rounding for every tested spectrum
+constexpr int kJacobiSweepsF64 = 7;       // fp64 (K2L only): two more quadratic sweeps reach 1e-16
 
-SUHPE_HD void jacobi_pair(float* bp, float* bq, float* vp, float* vq) {
-    const float alpha = fmaf(bp[0], bp[0], fmaf(bp[1], bp[1], bp[2] * bp[2]));
-    const float beta  = fmaf(bq[0], bq[0], fmaf(bq[1], bq[1], bq[2] * bq[2]));
-    const float gamma = fmaf(bp[0], bq[0], fmaf(bp[1], bq[1], bp[2] * bq[2]));
-    const float d  = beta - alpha;
-    const float g2 = gamma + gamma;
-    const float h  = sqrt_rn(fmaf(d, d, g2 * g2));
-    const float den = fabsf(d) + h;
+// scalar-type shims so the same source instantiates in fp32 (every kernel) and fp64 (K2L's
+// per-sample set-up, where the Laplace NLL cancels sum(s) against <A,R>)
+SUHPE_HD float  fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+SUHPE_HD double fma_t(double a, double b, double c) { return fma(a, b, c); }
+SUHPE_HD float  sqrt_t(float a) { return sqrt_rn(a); }
+SUHPE_HD double sqrt_t(double a) { return sqrt(a); }
+SUHPE_HD float  div_t(float a, float b) { return div_rn(a, b); }
+SUHPE_HD double div_t(double a, double b) { return a / b; }
+SUHPE_HD float  abs_t(float a) { return fabsf(a); }
+SUHPE_HD double abs_t(double a) { return fabs(a); }
+
+template <typename T>
+SUHPE_HD void jacobi_pair(T* bp, T* bq, T* vp, T* vq, T skip) {
+    const T alpha = fma_t(bp[0], bp[0], fma_t(bp[1], bp[1], bp[2] * bp[2]));
+    const T beta  = fma_t(bq[0], bq[0], fma_t(bq[1], bq[1], bq[2] * bq[2]));
+    const T gamma = fma_t(bp[0], bq[0], fma_t(bp[1], bq[1], bp[2] * bq[2]));
+    const T d  = beta - alpha;
+    const T g2 = gamma + gamma;
+    const T h  = sqrt_t(fma_t(d, d, g2 * g2));
+    const T den = abs_t(d) + h;
     // tan(theta) = sgn(d) 2 gamma / (|d| + sqrt(d^2 + 4 gamma^2)); 0 when already orthogonal
-    float t = (den > 0.0f) ? div_rn((d < 0.0f) ? -g2 : g2, den) : 0.0f;
+    T t = (den > T(0)) ? div_t((d < T(0)) ? -g2 : g2, den) : T(0);
     // rotations below the rounding level of the columns are skipped (also avoids
     // denormal-driven drift when gamma ~ 0)
-    if (gamma * gamma <= 1e-16f * alpha * beta) t = 0.0f;
-    const float c = div_rn(1.0f, sqrt_rn(fmaf(t, t, 1.0f)));
-    const float s = t * c;
+    if (gamma * gamma <= skip * alpha * beta) t = T(0);
+    const T c = div_t(T(1), sqrt_t(fma_t(t, t, T(1))));
+    const T s = t * c;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const float x = bp[i], y = bq[i];
-        bp[i] = fmaf(c, x, -s * y);
-        bq[i] = fmaf(s, x, c * y);
-        const float vx = vp[i], vy = vq[i];
-        vp[i] = fmaf(c, vx, -s * vy);
-        vq[i] = fmaf(s, vx, c * vy);
+        const T x = bp[i], y = bq[i];
+        bp[i] = fma_t(c, x, -s * y);
+        bq[i] = fma_t(s, x, c * y);
+        const T vx = vp[i], vy = vq[i];
+        vp[i] = fma_t(c, vx, -s * vy);
+        vq[i] = fma_t(s, vx, c * vy);
     }
 }
 
 // swap columns p,q as the rotation (bp,bq) <- (bq,-bp): keeps det V = +1
-SUHPE_HD void rot_swap(bool doit, float* bp, float* bq, float* vp, float* vq, float& np_, float& nq_) {
+template <typename T>
+SUHPE_HD void rot_swap(bool doit, T* bp, T* bq, T* vp, T* vq, T& np_, T& nq_) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const float x = bp[i], y = bq[i];
+        const T x = bp[i], y = bq[i];
         bp[i] = doit ? y : x;
         bq[i] = doit ? -x : y;
-        const float vx = vp[i], vy = vq[i];
+        const T vx = vp[i], vy = vq[i];
         vp[i] = doit ? vy : vx;
         vq[i] = doit ? -vx : vy;
     }
-    const float a = np_, b = nq_;
+    const T a = np_, b = nq_;
     np_ = doit ? b : a;
     nq_ = doit ? a : b;
 }
 
-// A, U, V row-major 3x3.  Returns false when A holds a non-finite value
+// A (fp32 input), U, V row-major 3x3 in T.  Returns false when A holds a non-finite value
 // (the reference's torch.svd raises in that case).
-SUHPE_HD bool proper_svd3(const float* A, float* U, float* V, float* s) {
+template <typename T>
+SUHPE_HD bool proper_svd3_t(const float* A, T* U, T* V, T* s) {
+    constexpr bool kF64 = sizeof(T) == 8;
     float amax = 0.0f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) amax = fmaxf(amax, fabsf(A[i]));
@@ -158,57 +174,58 @@ SUHPE_HD bool proper_svd3(const float* A, float* U, float* V, float* s) {
         down = a.f; up = b.f;
 #endif
     }
-    // column vectors of the scaled matrix
-    float b0[3] = {A[0] * down, A[3] * down, A[6] * down};
-    float b1[3] = {A[1] * down, A[4] * down, A[7] * down};
-    float b2[3] = {A[2] * down, A[5] * down, A[8] * down};
-    float v0[3] = {1.f, 0.f, 0.f}, v1[3] = {0.f, 1.f, 0.f}, v2[3] = {0.f, 0.f, 1.f};
+    // column vectors of the scaled matrix (the scaling is exact in either precision)
+    T b0[3] = {T(A[0] * down), T(A[3] * down), T(A[6] * down)};
+    T b1[3] = {T(A[1] * down), T(A[4] * down), T(A[7] * down)};
+    T b2[3] = {T(A[2] * down), T(A[5] * down), T(A[8] * down)};
+    T v0[3] = {T(1), T(0), T(0)}, v1[3] = {T(0), T(1), T(0)}, v2[3] = {T(0), T(0), T(1)};
+    const T skip = kF64 ? T(1e-32) : T(1e-16f);
 #pragma unroll 1
-    for (int sweep = 0; sweep < kJacobiSweeps; ++sweep) {
-        jacobi_pair(b0, b1, v0, v1);
-        jacobi_pair(b0, b2, v0, v2);
-        jacobi_pair(b1, b2, v1, v2);
+    for (int sweep = 0; sweep < (kF64 ? kJacobiSweepsF64 : kJacobiSweeps); ++sweep) {
+        jacobi_pair(b0, b1, v0, v1, skip);
+        jacobi_pair(b0, b2, v0, v2, skip);
+        jacobi_pair(b1, b2, v1, v2, skip);
     }
-    float n0 = fmaf(b0[0], b0[0], fmaf(b0[1], b0[1], b0[2] * b0[2]));
-    float n1 = fmaf(b1[0], b1[0], fmaf(b1[1], b1[1], b1[2] * b1[2]));
-    float n2 = fmaf(b2[0], b2[0], fmaf(b2[1], b2[1], b2[2] * b2[2]));
+    T n0 = fma_t(b0[0], b0[0], fma_t(b0[1], b0[1], b0[2] * b0[2]));
+    T n1 = fma_t(b1[0], b1[0], fma_t(b1[1], b1[1], b1[2] * b1[2]));
+    T n2 = fma_t(b2[0], b2[0], fma_t(b2[1], b2[1], b2[2] * b2[2]));
     rot_swap(n0 < n1, b0, b1, v0, v1, n0, n1);
     rot_swap(n0 < n2, b0, b2, v0, v2, n0, n2);
     rot_swap(n1 < n2, b1, b2, v1, v2, n1, n2);
 
     // left vectors: u0 = b0/|b0|, u1 = normalised (b1 - (b1.u0)u0), u2 = u0 x u1
-    float u0[3], u1[3], u2[3];
-    const float sig0 = sqrt_rn(n0);
-    if (sig0 > 0.0f) {
-        const float inv = div_rn(1.0f, sig0);
+    T u0[3], u1[3], u2[3];
+    const T sig0 = sqrt_t(n0);
+    if (sig0 > T(0)) {
+        const T inv = div_t(T(1), sig0);
         u0[0] = b0[0] * inv; u0[1] = b0[1] * inv; u0[2] = b0[2] * inv;
     } else {
-        u0[0] = 1.f; u0[1] = 0.f; u0[2] = 0.f;
+        u0[0] = T(1); u0[1] = T(0); u0[2] = T(0);
     }
-    const float p = fmaf(b1[0], u0[0], fmaf(b1[1], u0[1], b1[2] * u0[2]));
-    float w[3] = {fmaf(-p, u0[0], b1[0]), fmaf(-p, u0[1], b1[1]), fmaf(-p, u0[2], b1[2])};
-    float nw = fmaf(w[0], w[0], fmaf(w[1], w[1], w[2] * w[2]));
-    if (!(nw > 1e-30f)) {
+    const T p = fma_t(b1[0], u0[0], fma_t(b1[1], u0[1], b1[2] * u0[2]));
+    T w[3] = {fma_t(-p, u0[0], b1[0]), fma_t(-p, u0[1], b1[1]), fma_t(-p, u0[2], b1[2])};
+    T nw = fma_t(w[0], w[0], fma_t(w[1], w[1], w[2] * w[2]));
+    if (!(nw > T(1e-30))) {
         // rank <= 1: any unit vector orthogonal to u0 (axis least aligned with u0)
-        const float a0 = fabsf(u0[0]), a1 = fabsf(u0[1]), a2 = fabsf(u0[2]);
+        const T a0 = abs_t(u0[0]), a1 = abs_t(u0[1]), a2 = abs_t(u0[2]);
         const int k = (a1 <= a0 && a1 <= a2) ? 1 : ((a2 <= a0 && a2 <= a1) ? 2 : 0);
-        const float uk = (k == 0) ? u0[0] : ((k == 1) ? u0[1] : u0[2]);
-        w[0] = ((k == 0) ? 1.f : 0.f) - uk * u0[0];
-        w[1] = ((k == 1) ? 1.f : 0.f) - uk * u0[1];
-        w[2] = ((k == 2) ? 1.f : 0.f) - uk * u0[2];
-        nw = fmaf(w[0], w[0], fmaf(w[1], w[1], w[2] * w[2]));
+        const T uk = (k == 0) ? u0[0] : ((k == 1) ? u0[1] : u0[2]);
+        w[0] = ((k == 0) ? T(1) : T(0)) - uk * u0[0];
+        w[1] = ((k == 1) ? T(1) : T(0)) - uk * u0[1];
+        w[2] = ((k == 2) ? T(1) : T(0)) - uk * u0[2];
+        nw = fma_t(w[0], w[0], fma_t(w[1], w[1], w[2] * w[2]));
     }
     {
-        const float inv = div_rn(1.0f, sqrt_rn(nw));
+        const T inv = div_t(T(1), sqrt_t(nw));
         u1[0] = w[0] * inv; u1[1] = w[1] * inv; u1[2] = w[2] * inv;
     }
-    u2[0] = fmaf(u0[1], u1[2], -u0[2] * u1[1]);
-    u2[1] = fmaf(u0[2], u1[0], -u0[0] * u1[2]);
-    u2[2] = fmaf(u0[0], u1[1], -u0[1] * u1[0]);
+    u2[0] = fma_t(u0[1], u1[2], -u0[2] * u1[1]);
+    u2[1] = fma_t(u0[2], u1[0], -u0[0] * u1[2]);
+    u2[2] = fma_t(u0[0], u1[1], -u0[1] * u1[0]);
 
-    s[0] = sig0 * up;
-    s[1] = fmaf(b1[0], u1[0], fmaf(b1[1], u1[1], b1[2] * u1[2])) * up;
-    s[2] = fmaf(b2[0], u2[0], fmaf(b2[1], u2[1], b2[2] * u2[2])) * up;
+    s[0] = sig0 * T(up);
+    s[1] = fma_t(b1[0], u1[0], fma_t(b1[1], u1[1], b1[2] * u1[2])) * T(up);
+    s[2] = fma_t(b2[0], u2[0], fma_t(b2[1], u2[1], b2[2] * u2[2])) * T(up);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         U[3 * i + 0] = u0[i]; U[3 * i + 1] = u1[i]; U[3 * i + 2] = u2[i];
@@ -216,6 +233,8 @@ SUHPE_HD bool proper_svd3(const float* A, float* U, float* V, float* s) {
     }
     return finite;
 }
+
+SUHPE_HD bool proper_svd3(const float* A, float* U, float* V, float* s) { return proper_svd3_t<float>(A, U, V, s); }
 
 // R = U diag(d0,d1,d2) V^T  (row-major)
 SUHPE_HD void u_diag_vt(const float* U, const float* V, float d0, float d1, float d2, float* R) {
@@ -226,6 +245,22 @@ SUHPE_HD void u_diag_vt(const float* U, const float* V, float d0, float d1, floa
         for (int j = 0; j < 3; ++j)
             R[3 * i + j] = fmaf(a, V[3 * j + 0], fmaf(b, V[3 * j + 1], c * V[3 * j + 2]));
     }
+}
+
+// K2L per-sample set-up in fp64: mode R* = U V^T (rounded to fp32) and T = s1 + s2 + s3 (proper,
+// signed) as a double.  The Laplace NLL subtracts <A,R> from T (src/laplace/rotation_laplace.py:
+// 161-170); carrying T and the ground-truth term in fp64 keeps that cancellation exact to fp32
+// rounding for the cost of one 3x3 Jacobi per sample (the grid loop is ~5,000x more work).
+SUHPE_HD bool laplace_setup(const float* A, float* Rs, double* T) {
+    double U[9], V[9], s[3];
+    const bool ok = proper_svd3_t<double>(A, U, V, s);
+    *T = s[0] + s[1] + s[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Rs[3 * i + j] = (float)fma(U[3 * i], V[3 * j], fma(U[3 * i + 1], V[3 * j + 1], U[3 * i + 2] * V[3 * j + 2]));
+    return ok;
 }
 
 // ----------------------------------------------------------------------------
@@ -504,6 +539,96 @@ SUHPE_HD FisherStats fisher_finish(const float* s, float F, float N0, float N1, 
     // Fisher->Bingham->autograd chain (src/fisher/fisher_utils.py:70-81)
     o.entropy = o.logf + fmaf(s[0], 1.0f - o.g[0], fmaf(s[1], 1.0f - o.g[1], s[2] * (1.0f - o.g[2])));
     return o;
+}
+
+// ----------------------------------------------------------------------------
+// Rotation-Laplace grid sum (src/laplace/rotation_laplace.py:58-72,140-173 and its autograd
+// backward).  Per (sample, grid point k):
+//   d_k = T - <A,R_k>,  q_k = sqrt(max(d_k, 1e-8)),  w_k = exp(-q_k)/q_k
+//   Z = sum w_k,  C = sum w_k (1/q_k + 1/q_k^2) [live points],  M = sum (same weight) R_k
+// kept relative to the running minimum of q (the reference subtracts c = max_k(-q_k) first).
+// ----------------------------------------------------------------------------
+constexpr float kLapEps = 1e-8f;           // rotation_laplace.py:11
+
+// Two-level sums: points add into the block sums (z, c, m); laplace_accum_flush() folds a block
+// into the totals (Z, C, M).  The thread-per-sample decomposition flushes every 128 points, so its
+// fp32 summation error matches the warp-per-sample one (32 lane partials) instead of growing with
+// the 4608-point grid -- the gradient subtracts sum(chat_k) R* from sum(chat_k R_k) and amplifies it.
+struct LaplaceAccum { float qmin, Z, C, M[9], z, c, m[9]; };
+
+SUHPE_HD void laplace_accum_init(LaplaceAccum& a) {
+    a.qmin = INFINITY; a.Z = a.C = a.z = a.c = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a.M[i] = a.m[i] = 0.f;
+}
+
+// sqrt with one Newton step on top of MUFU.RSQ: q ~ sqrt(d), rs ~ 1/sqrt(d)
+SUHPE_HD void sqrt_pair(float d, float& q, float& rs) {
+    rs = mufu_rsqrt(d);
+    q = d * rs;
+    const float err = fmaf(-q, q, d);
+    q = fmaf(0.5f * rs, err, q);
+}
+
+SUHPE_HD void laplace_accum_scale(LaplaceAccum& a, float sc) {
+    a.Z *= sc; a.C *= sc; a.z *= sc; a.c *= sc;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { a.M[i] *= sc; a.m[i] *= sc; }
+}
+
+SUHPE_HD void laplace_accum_point(LaplaceAccum& a, const float* A, float T, const float* r) {
+    float t = A[0] * r[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) t = fmaf(A[i], r[i], t);
+    const float d = T - t;
+    const bool live = d >= kLapEps;          // clamp_min passes the gradient where input >= min
+    float q, rs;
+    sqrt_pair(fmaxf(d, kLapEps), q, rs);
+    if (q < a.qmin) {                         // new running maximum of p = -q: rescale (rare)
+        laplace_accum_scale(a, mufu_ex2((q - a.qmin) * kLog2e));
+        a.qmin = q;
+    }
+    const float w = mufu_ex2((a.qmin - q) * kLog2e) * rs;    // exp(p - c) / (-p)
+    a.z += w;
+    const float cw = live ? w * fmaf(rs, rs, rs) : 0.0f;      // w (1/q + 1/q^2); the 1/2 is applied once at the end
+    a.c += cw;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a.m[i] = fmaf(cw, r[i], a.m[i]);
+}
+
+SUHPE_HD void laplace_accum_flush(LaplaceAccum& a) {
+    a.Z += a.z; a.C += a.c; a.z = a.c = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { a.M[i] += a.m[i]; a.m[i] = 0.f; }
+}
+
+// re-express a (flushed) partial accumulator relative to a smaller or equal minimum qg before merging partials
+SUHPE_HD void laplace_accum_rebase(LaplaceAccum& a, float qg) {
+    laplace_accum_scale(a, (a.qmin == INFINITY) ? 0.f : mufu_ex2((qg - a.qmin) * kLog2e));
+    a.qmin = qg;
+}
+
+// nll = logF + q_x + log q_x,  d nll/dA = -sum_k chat_k (R* - R_k) + c_x (R* - R_gt);
+// dx = T - <A,R_gt> comes in already cancelled in fp64 (laplace_setup)
+SUHPE_HD void laplace_finish(const LaplaceAccum& a, float dx, const float* Rs, const float* Rg, int N,
+                             float* nll, float* logF_out, float* grad) {
+    // logF = c + log(sum * (1/N)), c = -qmin   (rotation_laplace.py:69-71)
+    const float logF = -a.qmin + logf(a.Z * (1.0f / (float)N));
+    const float qx = sqrt_rn(fmaxf(dx, kLapEps));
+    *nll = logF + qx + logf(qx);
+    *logF_out = logF;
+    const float invZ = 0.5f / a.Z;
+    const float cs = a.C * invZ;                                   // sum_k chat_k
+    const float cx = (dx >= kLapEps) ? 0.5f * (1.0f + 1.0f / qx) / qx : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) grad[i] = fmaf(a.M[i], invZ, fmaf(cx - cs, Rs[i], -cx * Rg[i]));
+}
+
+SUHPE_HD float laplace_gt_gap(const float* A, const float* Rg, double T) {
+    double tx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tx = fma((double)A[i], (double)Rg[i], tx);
+    return (float)(T - tx);
 }
 
 // ----------------------------------------------------------------------------

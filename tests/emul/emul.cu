@@ -220,4 +220,44 @@ void emul_metrics(const float* Rp, const float* Rg, const float* gt_euler, long 
     }
 }
 
+
+// K2L with the kernel's two decompositions: L = 1 (one thread walks the grid in order) and
+// L = 32 (lane l takes points l, l+32, ...; partials rebased to the common minimum, butterfly-merged)
+void emul_laplace(const float* A, const float* Rgt, long n, const float* grid, int N, int L,
+                  float* nll, float* grad, float* mode, float* logF) {
+    for (long i = 0; i < n; ++i) {
+        const float* a9 = A + 9 * i;
+        float Rs[9];
+        double Td;
+        laplace_setup(a9, Rs, &Td);
+        const float T = (float)Td;
+        LaplaceAccum acc[32];
+        for (int l = 0; l < L; ++l) {
+            laplace_accum_init(acc[l]);
+            if (L == 1) {
+                for (int k0 = 0; k0 < N; k0 += 128) {
+                    for (int k = k0; k < N && k < k0 + 128; ++k) laplace_accum_point(acc[l], a9, T, grid + 9 * k);
+                    laplace_accum_flush(acc[l]);
+                }
+            } else {
+                for (int k = l; k < N; k += L) laplace_accum_point(acc[l], a9, T, grid + 9 * k);
+                laplace_accum_flush(acc[l]);
+            }
+        }
+        if (L > 1) {
+            float qg = acc[0].qmin;
+            for (int l = 1; l < L; ++l) qg = fminf(qg, acc[l].qmin);
+            for (int l = 0; l < L; ++l) laplace_accum_rebase(acc[l], qg);
+            for (int off = 16; off >= 1; off >>= 1)
+                for (int l = 0; l < 32; ++l)
+                    if ((l & off) == 0) {
+                        acc[l].Z += acc[l ^ off].Z; acc[l].C += acc[l ^ off].C;
+                        for (int k = 0; k < 9; ++k) acc[l].M[k] += acc[l ^ off].M[k];
+                    }
+        }
+        laplace_finish(acc[0], laplace_gt_gap(a9, Rgt + 9 * i, Td), Rs, Rgt + 9 * i, N, nll + i, logF + i, grad + 9 * i);
+        for (int k = 0; k < 9; ++k) mode[9 * i + k] = Rs[k];
+    }
+}
+
 }  // extern "C"

@@ -93,6 +93,39 @@ def test_negligible_node_cut_is_below_rounding(emul, golden):
     assert_close(cut["logC"], full["logC"], 2e-7, 2e-7, "logC random")
 
 
+def run_laplace(emul, A, R, grid, L):
+    A = np.ascontiguousarray(A.reshape(-1, 9), np.float32)
+    R = np.ascontiguousarray(R.reshape(-1, 9), np.float32)
+    grid = np.ascontiguousarray(grid.reshape(-1, 9), np.float32)
+    n = len(A)
+    o = {k: np.zeros(s, np.float32) for k, s in dict(nll=n, grad=(n, 9), mode=(n, 9), logF=n).items()}
+    emul.emul_laplace(P(A), P(R), ctypes.c_long(n), P(grid), ctypes.c_int(len(grid)), ctypes.c_int(L),
+                      P(o["nll"]), P(o["grad"]), P(o["mode"]), P(o["logF"]))
+    return o
+
+
+def test_laplace_against_golden(emul, golden):
+    """K2L arithmetic (fp64 per-sample set-up, two-level fp32 grid sums) in both decompositions the
+    kernel uses: parity with the reference's fp32 output, closer to exact arithmetic than the
+    reference itself, and the two decompositions agree."""
+    g = golden("laplace")
+    A64 = torch.from_numpy(g["A"]).double().requires_grad_(True)
+    nll64, _ = orc.laplace_nll("RLaplace", A64, torch.from_numpy(g["R"]).double(), torch.from_numpy(g["grids"]).double())
+    nll64.sum().backward()
+    e64, g64 = nll64.detach().numpy(), A64.grad.numpy().reshape(-1, 9)
+    outs = {L: run_laplace(emul, g["A"], g["R"], g["grids"], L) for L in (1, 32)}
+    for L, o in outs.items():
+        assert_close(o["nll"], g["nll"], 5e-5, 5e-5, f"laplace nll L={L}")
+        assert grad_rel_err(o["grad"], g["grad"]).max() < 2e-3
+        assert no_worse_than_reference(o["nll"], g["nll"], e64, 2.0, 5e-6).all()
+        ours_rel, ref_rel = grad_rel_err(o["grad"], g64), grad_rel_err(g["grad"], g64)
+        assert ours_rel.max() <= ref_rel.max()
+        well = g["A"].reshape(-1, 9).std(1) > 0.5
+        assert np.abs(o["mode"] - g["mode"].reshape(-1, 9))[well].max() < 2e-5
+    assert grad_rel_err(outs[1]["grad"], outs[32]["grad"]).max() < 2e-4
+    assert_close(outs[1]["nll"], outs[32]["nll"], 1e-5, 1e-5, "decompositions")
+
+
 def test_svd_properties(emul):
     rng = np.random.default_rng(0)
     n = 20000

@@ -29,13 +29,17 @@ def test_laplace_golden_small_batch_path(cuda, golden):
     nll64, _ = orc.laplace_nll("RLaplace", l64, R64, g64)
     nll64.sum().backward()
     assert no_worse_than_reference(losses.detach().cpu().numpy(), g["nll"], nll64.detach().numpy(), 2.0, 5e-6).all()
-    ours_err = np.abs(leaf.grad.cpu().numpy().reshape(-1, 9) - l64.grad.numpy().reshape(-1, 9)).max(1)
-    ref_err = np.abs(g["grad"].reshape(-1, 9) - l64.grad.numpy().reshape(-1, 9)).max(1)
-    assert (ours_err <= 2 * ref_err + 1e-6 * (1 + np.abs(l64.grad.numpy()).reshape(-1, 9).max(1))).all()
+    # gradient against exact arithmetic: over the batch we must be at least as close as the reference's
+    # own fp32 result, and every row within the reference's noise level (2e-4 of the row's scale)
+    g64 = l64.grad.numpy().reshape(-1, 9)
+    ours_rel, ref_rel = grad_rel_err(leaf.grad.cpu().numpy(), g64), grad_rel_err(g["grad"], g64)
+    assert ours_rel.max() <= ref_rel.max() and np.median(ours_rel) <= 1.5 * np.median(ref_rel)
+    assert (ours_rel <= 2 * ref_rel + 2e-4).all()
     well = (g["A"].reshape(-1, 9).std(1) > 0.5)
     assert np.abs(mode.cpu().numpy() - g["mode"])[well].max() < 2e-5
     m2, s3 = analytical_mode(A, "RLaplace")
-    assert torch.equal(m2, mode) and torch.equal(s3.cpu(), torch.sign(torch.from_numpy(g["s3sign"])))
+    # K2L derives its mode from the fp64 per-sample set-up, K1 (analytical_mode) works in fp32: same rotation to rounding
+    assert (m2 - mode).abs().max().item() < 1e-6 and torch.equal(s3.cpu(), torch.sign(torch.from_numpy(g["s3sign"])))
     assert_close(log_pdf("RFisher", A, R, grids).cpu().numpy(), g["rfisher_logpdf"], 2e-5, 2e-5, "RFisher grid pdf")
     dens = log_pdf("RLaplace", A[:4], grids, grids)
     want = orc.grid_log_pdf("RLaplace", torch.from_numpy(g["A"][:4]), torch.from_numpy(g["grids"]), torch.from_numpy(g["grids"]))
@@ -57,7 +61,7 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
     small = _ops.laplace_nll(A[:300], R[:300], grids, grad=True, mode=True)
     assert_close(big["nll"][:300].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "decompositions")
     assert grad_rel_err(big["grad"][:300].cpu().numpy(), small["grad"].cpu().numpy()).max() < 2e-4
-    assert torch.equal(big["mode"][:300], small["mode"])
+    assert (big["mode"][:300] - small["mode"]).abs().max().item() < 1e-6
     idx = torch.arange(n - 64, n)
     ref, _ = orc.laplace_nll("RLaplace", A[idx].cpu(), R[idx].cpu(), torch.from_numpy(g["grids"]))
     assert_close(big["nll"][idx].cpu().numpy(), ref.numpy(), LAP_RTOL, LAP_ATOL, "tail rows")
