@@ -381,16 +381,17 @@ def run_e2e(torch, dist, dev, n, args, world, rank):
     q = q / q.norm(dim=1, keepdim=True)
     from semiuhpe_b200.agent import _quat_to_matrix
     R_h = _quat_to_matrix(q).reshape(n, 9).contiguous().pin_memory()
-    pipe = FisherFilterPipeline(max_n=n, chunk=1 << 20, device=dev.index)
-    res = pipe.run(A_h, R_h, OVERREG, LEFT_RATIO)          # warm-up (allocates pinned outputs)
-    pipe.run(A_h, R_h, OVERREG, LEFT_RATIO)
+    pipe = FisherFilterPipeline(max_n=n, chunk=args.e2e_chunk, device=dev.index)
+    group = True if world > 1 else None                    # N > 1: global threshold over all ranks' shards
+    res = pipe.run(A_h, R_h, OVERREG, LEFT_RATIO, group=group)   # warm-up (allocates pinned outputs)
+    pipe.run(A_h, R_h, OVERREG, LEFT_RATIO, group=group)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     steps = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = pipe.run(A_h, R_h, OVERREG, LEFT_RATIO)      # blocking call: results are on the host on return
+        res = pipe.run(A_h, R_h, OVERREG, LEFT_RATIO, group=group)   # blocking call: results are on the host on return
     dt = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
@@ -398,8 +399,12 @@ def run_e2e(torch, dist, dev, n, args, world, rank):
         dt = float(t.item())
     out = {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": res["h2d_bytes"],
            "d2h_bytes_per_step": res["d2h_bytes"], "steps": steps, "ms_per_step": 1e3 * dt / steps,
-           "api": "semiuhpe_b200.host_pipeline.FisherFilterPipeline.run -> suhpe_fisher_filter_host (1 Mi-pair chunks, 2 streams)",
-           "note": "all ranks concurrently, max over ranks; the threshold in this leg is per-rank" if world > 1 else "single GPU"}
+           "api": ("semiuhpe_b200.host_pipeline.FisherFilterPipeline.run -> "
+                   + ("suhpe_fisher_pool_host + all-gathered radix select + mask" if world > 1 else "suhpe_fisher_filter_host")
+                   + f" ({args.e2e_chunk}-pair chunks, H2D / kernel / D2H queues over 4 buffers)"),
+           "threshold": res["threshold"], "kept": res["kept"],
+           "note": "all ranks concurrently (they share the host's PCIe/memory system), max over ranks; global threshold"
+                   if world > 1 else "single GPU"}
     pipe.close()
     return out
 
@@ -463,6 +468,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 20, help="pairs per chunk of the host-buffer pipeline")
     ap.add_argument("--skip-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")

@@ -125,16 +125,29 @@ int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks
 
 /* Host-buffer pipeline (what bench.py's e2e leg and a non-torch host would call):
  * the teacher-side filter step over a pool of n (A,Rgt) pairs living in HOST memory
- * (pinned for full PCIe rate).  Chunks are copied H2D, run through K2 (+fused first
- * histogram) and copied back D2H on alternating streams; then K3 selects the k-th
+ * (pinned for full PCIe rate).  Chunks move through three in-order queues -- host->device
+ * copies, K2 (+fused first histogram), device->host copies -- over a ring of four chunk
+ * buffers, so both copy engines and the SMs are busy at once; then K3 selects the k-th
  * smallest entropy of the whole pool and the mask is emitted and copied back.
- * Host outputs nullable; threshold/kept written on return (the call blocks). */
+ * Replaces the per-batch loop of src/agent.py:357-417 (teacher forward -> fisher_entropy ->
+ * host sort).  Host outputs nullable; threshold/kept written on return (the call blocks). */
 typedef struct suhpe_pipeline suhpe_pipeline;
 int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk);
 int suhpe_pipeline_destroy(suhpe_pipeline* p);
 int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
                              float overreg, uint64_t k, float* nll_host, float* grad_host,
                              float* entropy_host, uint8_t* mask_host, float* threshold, uint64_t* kept);
+/* The same pipeline in two phases, for pools sharded over several GPUs: phase A streams this
+ * rank's shard through K2 and leaves the entropies in ent_dev (n), ADDS the first radix
+ * histogram into hist_dev (2048 counters, zeroed by the caller) and ORs status bits into
+ * status_dev (all caller-owned device memory).  Returns once everything is queued; `stream`
+ * is made to wait for the last kernel, so the caller queues the global select on it (K3 passes
+ * + an all-gather of the histograms, semiuhpe_b200/distributed.py) while the device->host copies
+ * drain.  suhpe_pipeline_sync blocks until the host buffers are complete. */
+int suhpe_fisher_pool_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
+                           float overreg, float* nll_host, float* grad_host, float* entropy_host,
+                           float* ent_dev, uint64_t* hist_dev, int* status_dev, void* stream);
+int suhpe_pipeline_sync(suhpe_pipeline* p);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,8 @@ SIGNATURES = {
     "suhpe_pipeline_destroy": (ctypes.c_int, [c_vp]),
     "suhpe_fisher_filter_host": (ctypes.c_int, [c_vp, c_vp, c_vp, i64, f32, u64, c_vp, c_vp, c_vp, c_vp,
                                                 ctypes.POINTER(f32), ctypes.POINTER(u64)]),
+    "suhpe_fisher_pool_host": (ctypes.c_int, [c_vp, c_vp, c_vp, i64, f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "suhpe_pipeline_sync": (ctypes.c_int, [c_vp]),
 }
 
 EINVAL = -100000

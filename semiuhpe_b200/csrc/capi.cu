@@ -164,10 +164,13 @@ cudaError_t launch_fp32_probe(float* sink, int variant, int iters, int blocks, c
 
 // ---- host-buffer pipeline ------------------------------------------------------
 struct suhpe_pipeline {
+    // Three in-order queues -- host->device copies, kernels, device->host copies -- over a ring of
+    // kBuffers chunk buffers, so the two copy engines and the SMs all stay busy at once.
+    static constexpr int kBuffers = 4;
     long long max_n, chunk;
-    cudaStream_t streams[2];
-    cudaEvent_t done[2];
-    float *dA[2], *dR[2], *dGrad[2], *dNll[2];
+    cudaStream_t s_in, s_k, s_out;
+    cudaEvent_t ev_in[kBuffers], ev_k[kBuffers], ev_out[kBuffers], ev_user;
+    float *dA[kBuffers], *dR[kBuffers], *dGrad[kBuffers], *dNll[kBuffers];
     float* dEnt;             // (max_n) entropies of the whole pool stay resident for the select
     uint8_t* dMask;          // (max_n)
     unsigned long long* dHist;   // 2 x SUHPE_HIST_BINS: [0] fused first pass, [1] scratch
@@ -309,9 +312,14 @@ int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks
 // ---- pipeline ---------------------------------------------------------------------
 int suhpe_pipeline_destroy(suhpe_pipeline* p) {
     if (!p) return 0;
-    for (int i = 0; i < 2; ++i) {
-        if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
-        if (p->done[i]) cudaEventDestroy(p->done[i]);
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_k) cudaStreamDestroy(p->s_k);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    if (p->ev_user) cudaEventDestroy(p->ev_user);
+    for (int i = 0; i < suhpe_pipeline::kBuffers; ++i) {
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_k[i]) cudaEventDestroy(p->ev_k[i]);
+        if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
         cudaFree(p->dA[i]); cudaFree(p->dR[i]); cudaFree(p->dGrad[i]); cudaFree(p->dNll[i]);
     }
     cudaFree(p->dEnt); cudaFree(p->dMask); cudaFree(p->dHist); cudaFree(p->dState); cudaFree(p->dStatus);
@@ -331,9 +339,11 @@ int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk) {
     p->max_n = max_n; p->chunk = chunk;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(q, bytes); };
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming);
+    auto S = [&](cudaStream_t* s) { if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); };
+    auto E = [&](cudaEvent_t* v) { if (e == cudaSuccess) e = cudaEventCreateWithFlags(v, cudaEventDisableTiming); };
+    S(&p->s_in); S(&p->s_k); S(&p->s_out); E(&p->ev_user);
+    for (int i = 0; i < suhpe_pipeline::kBuffers && e == cudaSuccess; ++i) {
+        E(&p->ev_in[i]); E(&p->ev_k[i]); E(&p->ev_out[i]);
         A((void**)&p->dA[i], (size_t)chunk * 36); A((void**)&p->dR[i], (size_t)chunk * 36);
         A((void**)&p->dGrad[i], (size_t)chunk * 36); A((void**)&p->dNll[i], (size_t)chunk * 4);
     }
@@ -347,52 +357,92 @@ int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk) {
     return 0;
 }
 
+// Phase A of the host pipeline: stream the pool through K2.  Entropies land in ent_dev (n),
+// the first radix histogram is ADDED into hist_dev (2048 counters the caller zeroed) and the
+// status bits are OR-ed into status_dev -- all three are caller-owned device buffers, ordered
+// against `stream`: the first kernel waits for work already queued on `stream`, and on return
+// `stream` waits for the last kernel, so a select (single-GPU, or the all-gather form over
+// NCCL) can be queued on it straight away while the device->host copies still drain.
+int suhpe_fisher_pool_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
+                           float overreg, float* nll_host, float* grad_host, float* entropy_host,
+                           float* ent_dev, uint64_t* hist_dev, int* status_dev, void* stream) {
+    if (!p || !A_host || !ent_dev || n <= 0 || n > p->max_n) return SUHPE_EINVAL;
+    constexpr int NB = suhpe_pipeline::kBuffers;
+    cudaStream_t user = st(stream);
+    const bool external = user != p->s_k;
+    cudaError_t e = cudaSuccess;
+#define CK(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    if (external) {
+        CK(cudaEventRecord(p->ev_user, user));
+        CK(cudaStreamWaitEvent(p->s_k, p->ev_user, 0));
+    }
+    const long long nchunks = (n + p->chunk - 1) / p->chunk;
+    for (long long c = 0; c < nchunks && e == cudaSuccess; ++c) {
+        const int b = (int)(c % NB);
+        const long long base = c * p->chunk;
+        const long long cnt = (n - base < p->chunk) ? (n - base) : p->chunk;
+        // inputs: the buffer is free once the kernel of its previous chunk has run
+        if (c >= NB) CK(cudaStreamWaitEvent(p->s_in, p->ev_k[b], 0));
+        CK(cudaMemcpyAsync(p->dA[b], A_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
+        if (Rgt_host) CK(cudaMemcpyAsync(p->dR[b], Rgt_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
+        CK(cudaEventRecord(p->ev_in[b], p->s_in));
+        // kernel: after its inputs landed and the previous outputs of this buffer were drained
+        CK(cudaStreamWaitEvent(p->s_k, p->ev_in[b], 0));
+        if (c >= NB) CK(cudaStreamWaitEvent(p->s_k, p->ev_out[b], 0));
+        FisherArgs a{};
+        a.A = p->dA[b]; a.Rgt = Rgt_host ? p->dR[b] : nullptr; a.n = cnt; a.overreg = overreg;
+        a.nll = nll_host ? p->dNll[b] : nullptr;
+        a.grad = grad_host ? p->dGrad[b] : nullptr;
+        a.entropy = ent_dev + base;
+        a.hist = reinterpret_cast<unsigned long long*>(hist_dev); a.status = status_dev; a.cut_bits = g_cut_bits;
+        CK(launch_fisher_fused(a, p->s_k));
+        CK(cudaEventRecord(p->ev_k[b], p->s_k));
+        // outputs
+        CK(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0));
+        if (nll_host) CK(cudaMemcpyAsync(nll_host + base, p->dNll[b], (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
+        if (grad_host) CK(cudaMemcpyAsync(grad_host + base * 9, p->dGrad[b], (size_t)cnt * 36, cudaMemcpyDeviceToHost, p->s_out));
+        if (entropy_host) CK(cudaMemcpyAsync(entropy_host + base, ent_dev + base, (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
+        CK(cudaEventRecord(p->ev_out[b], p->s_out));
+    }
+    if (external) CK(cudaStreamWaitEvent(user, p->ev_k[(nchunks - 1) % NB], 0));
+#undef CK
+    return rc(e);
+}
+
+// Blocks until every copy and kernel the pipeline queued has finished.
+int suhpe_pipeline_sync(suhpe_pipeline* p) {
+    if (!p) return SUHPE_EINVAL;
+    cudaError_t e = cudaStreamSynchronize(p->s_k);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_in);
+    return rc(e);
+}
+
 int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
                              float overreg, uint64_t k, float* nll_host, float* grad_host,
                              float* entropy_host, uint8_t* mask_host, float* threshold, uint64_t* kept) {
     if (!p || !A_host || n <= 0 || n > p->max_n || k >= (uint64_t)n) return SUHPE_EINVAL;
     cudaError_t e = cudaSuccess;
 #define CK(x) do { if (e == cudaSuccess) e = (x); } while (0)
-    cudaStream_t s0 = p->streams[0], s1 = p->streams[1];
-    CK(cudaMemsetAsync(p->dHist, 0, sizeof(unsigned long long) * 2 * SUHPE_HIST_BINS, s0));
-    CK(cudaMemsetAsync(p->dStatus, 0, sizeof(int), s0));
-    CK(cudaEventRecord(p->done[0], s0));
-    CK(cudaStreamWaitEvent(s1, p->done[0], 0));
-    long long nchunks = (n + p->chunk - 1) / p->chunk;
-    for (long long c = 0; c < nchunks && e == cudaSuccess; ++c) {
-        const int b = (int)(c & 1);
-        cudaStream_t s = p->streams[b];
-        const long long base = c * p->chunk;
-        const long long cnt = (n - base < p->chunk) ? (n - base) : p->chunk;
-        CK(cudaMemcpyAsync(p->dA[b], A_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, s));
-        if (Rgt_host) CK(cudaMemcpyAsync(p->dR[b], Rgt_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, s));
-        FisherArgs a{};
-        a.A = p->dA[b]; a.Rgt = Rgt_host ? p->dR[b] : nullptr; a.n = cnt; a.overreg = overreg;
-        a.nll = nll_host ? p->dNll[b] : nullptr;
-        a.grad = grad_host ? p->dGrad[b] : nullptr;
-        a.entropy = p->dEnt + base;
-        a.hist = p->dHist; a.status = p->dStatus; a.cut_bits = g_cut_bits;
-        CK(launch_fisher_fused(a, s));
-        if (nll_host) CK(cudaMemcpyAsync(nll_host + base, p->dNll[b], (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
-        if (grad_host) CK(cudaMemcpyAsync(grad_host + base * 9, p->dGrad[b], (size_t)cnt * 36, cudaMemcpyDeviceToHost, s));
-        if (entropy_host) CK(cudaMemcpyAsync(entropy_host + base, p->dEnt + base, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
-    }
-    // join stream 1 into stream 0, then select + mask on the resident entropies
-    CK(cudaEventRecord(p->done[1], s1));
-    CK(cudaStreamWaitEvent(s0, p->done[1], 0));
-    if (e == cudaSuccess) {
-        int r = suhpe_entropy_threshold_f32(p->dEnt, n, k, p->dState,
-                                            reinterpret_cast<uint64_t*>(p->dHist + SUHPE_HIST_BINS),
-                                            reinterpret_cast<const uint64_t*>(p->dHist), s0);
-        if (r != 0) return r;
-    }
-    CK(launch_mask(p->dEnt, n, &p->dState->threshold, 0.f, mask_host ? p->dMask : nullptr, &p->dState->kept, s0));
-    if (mask_host) CK(cudaMemcpyAsync(mask_host, p->dMask, (size_t)n, cudaMemcpyDeviceToHost, s0));
-    CK(cudaMemcpyAsync(p->hState, p->dState, sizeof(SelectState), cudaMemcpyDeviceToHost, s0));
-    CK(cudaMemcpyAsync(p->hStatus, p->dStatus, sizeof(int), cudaMemcpyDeviceToHost, s0));
-    CK(cudaStreamSynchronize(s0));
+    CK(cudaMemsetAsync(p->dHist, 0, sizeof(unsigned long long) * 2 * SUHPE_HIST_BINS, p->s_k));
+    CK(cudaMemsetAsync(p->dStatus, 0, sizeof(int), p->s_k));
+    if (e != cudaSuccess) return rc(e);
+    int r = suhpe_fisher_pool_host(p, A_host, Rgt_host, n, overreg, nll_host, grad_host, entropy_host,
+                                   p->dEnt, reinterpret_cast<uint64_t*>(p->dHist), p->dStatus, p->s_k);
+    if (r != 0) return r;
+    // select + mask on the resident entropies, in order behind the last kernel
+    r = suhpe_entropy_threshold_f32(p->dEnt, n, k, p->dState,
+                                    reinterpret_cast<uint64_t*>(p->dHist + SUHPE_HIST_BINS),
+                                    reinterpret_cast<const uint64_t*>(p->dHist), p->s_k);
+    if (r != 0) return r;
+    CK(launch_mask(p->dEnt, n, &p->dState->threshold, 0.f, mask_host ? p->dMask : nullptr, &p->dState->kept, p->s_k));
+    if (mask_host) CK(cudaMemcpyAsync(mask_host, p->dMask, (size_t)n, cudaMemcpyDeviceToHost, p->s_k));
+    CK(cudaMemcpyAsync(p->hState, p->dState, sizeof(SelectState), cudaMemcpyDeviceToHost, p->s_k));
+    CK(cudaMemcpyAsync(p->hStatus, p->dStatus, sizeof(int), cudaMemcpyDeviceToHost, p->s_k));
 #undef CK
     if (e != cudaSuccess) return rc(e);
+    r = suhpe_pipeline_sync(p);
+    if (r != 0) return r;
     if (threshold) *threshold = p->hState->threshold;
     if (kept) *kept = p->hState->kept;
     return (*p->hStatus & SUHPE_STATUS_NONFINITE) ? 1 : 0;   // >0: completed, non-finite input seen

@@ -32,3 +32,21 @@ def test_pipeline_matches_device_path(cuda, n, chunk):
     assert np.array_equal(res["mask"].numpy(), e < thr)
     assert res["kept"] == int((e < thr).sum())
     pipe.close()
+
+
+def test_two_phase_pipeline_matches_single_call(cuda):
+    """suhpe_fisher_pool_host + select on the caller's stream (the form the sharded pool uses)
+    gives the results of the one-call entry; with one rank the 'global' threshold is the local one."""
+    from semiuhpe_b200.host_pipeline import FisherFilterPipeline
+    n = 200001
+    gen = torch.Generator().manual_seed(5)
+    A = (10 * torch.randn(n, 9, generator=gen)).pin_memory()
+    R = random_rotations(n, gen).reshape(n, 9).pin_memory()
+    pipe = FisherFilterPipeline(max_n=n, chunk=8192)
+    one = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in pipe.run(A, R, 1.025, 0.95).items()}
+    for _ in range(2):                                   # twice: buffers and events are reused
+        two = pipe.run(A, R, 1.025, 0.95, group=True)
+        for key in ("nll", "grad", "entropy", "mask"):
+            assert torch.equal(one[key], two[key]), key
+        assert one["threshold"] == two["threshold"] and one["kept"] == two["kept"]
+    pipe.close()
