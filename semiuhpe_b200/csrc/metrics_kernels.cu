@@ -9,6 +9,14 @@
 //                                         (a per-sample Python loop in the reference)
 //           eval.py:76-98,125-133         per-angle errors, geodesic, Frobenius, means
 //           pytorch3d so3_relative_angle  (restated; PARITY UNPINNED, see oracle/)
+//
+// Layout of the work: every warp is its own two-stage pipeline.  A tile is 32 consecutive
+// pairs = 1152 + 1152 (+ 384) contiguous, 16-byte aligned bytes; lane 0 fetches the warp's NEXT
+// tile with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on a per-warp mbarrier) while
+// the 32 lanes work on the current one out of shared memory (stride-9 word reads: no bank
+// conflicts).  No block-wide barrier anywhere; a thread spends ~250 instructions per pair
+// (branch-free atan2, Markstein division: so3_math.cuh), so the copy engine, not instruction
+// issue, sets the pace.  Ragged tail tiles and unaligned base pointers take plain loads.
 #include "kernels.cuh"
 #include "so3_math.cuh"
 
@@ -16,58 +24,106 @@ namespace suhpe {
 
 namespace {
 
-constexpr int kMetThreads = 256;
+constexpr int kMetWarps = 8;
+constexpr int kMetThreads = kMetWarps * 32;
+constexpr int kMetCtasPerSm = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ src, int floats, bool vec) {
-    if (vec) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = threadIdx.x; i < floats / 4; i += kMetThreads) d4[i] = __ldg(s4 + i);
-    } else {
-        for (int i = threadIdx.x; i < floats; i += kMetThreads) dst[i] = __ldg(src + i);
-    }
+struct __align__(16) MetStage {
+    float rp[288];
+    float rg[288];
+    float ge[96];
+};
+struct __align__(16) MetWarp {
+    MetStage st[2];
+    float eul[96];           // euler out, staged for float4 stores
+    float err[96];           // abs err out
+    unsigned long long bar[2];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, int floats, bool vec) {
-    if (vec) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = threadIdx.x; i < floats / 4; i += kMetThreads) d4[i] = s4[i];
-    } else {
-        for (int i = threadIdx.x; i < floats; i += kMetThreads) dst[i] = src[i];
-    }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> this CTA's shared memory, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kMetThreads)
+__device__ __forceinline__ void plain_tile(float* dst, const float* __restrict__ src, int floats, int lane) {
+    for (int i = lane; i < floats; i += 32) dst[i] = __ldg(src + i);
+}
+
+__global__ void __launch_bounds__(kMetThreads, kMetCtasPerSm)
 metrics_kernel(MetricsArgs p, bool vec_ok) {
-    __shared__ __align__(16) float sp[kMetThreads * 9];
-    __shared__ __align__(16) float sg[kMetThreads * 9];
-    __shared__ __align__(16) float se[kMetThreads * 3];   // gt euler in -> abs err out
-    __shared__ __align__(16) float so[kMetThreads * 3];   // euler out
-    __shared__ double red[6][kMetThreads / 32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    MetWarp& ws = reinterpret_cast<MetWarp*>(smem_raw)[warp];
 
-    const int t = threadIdx.x;
-    const long long tiles = (p.n + kMetThreads - 1) / kMetThreads;
+    const long long tiles = (p.n + 31) / 32;
+    const long long full_tiles = vec_ok ? p.n / 32 : 0;          // tiles the bulk path may fetch
+    const long long stride = (long long)gridDim.x * kMetWarps;
     const bool want_euler = p.euler || p.abs_err || p.mae || (p.sums && p.gt_euler);
+    const unsigned tx_bytes = 1152u + (p.Rg ? 1152u : 0u) + (p.gt_euler ? 384u : 0u);
     double acc[6] = {0, 0, 0, 0, 0, 0};
     bool bad = false;
 
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long base = tile * kMetThreads;
-        const int count = (int)min((long long)kMetThreads, p.n - base);
-        const bool full = vec_ok && count == kMetThreads;
-        stage_in(sp, p.Rp + base * 9, count * 9, full);
-        if (p.Rg) stage_in(sg, p.Rg + base * 9, count * 9, full);
-        if (p.gt_euler) stage_in(se, p.gt_euler + base * 3, count * 3, full);
-        __syncthreads();
-        if (t < count) {
+    const unsigned bar0 = smem_u32(&ws.bar[0]);
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto fetch = [&](long long tile, int s) {                    // lane 0 only
+        const unsigned bar = bar0 + 8u * s;
+        mbar_expect_tx(bar, tx_bytes);
+        bulk_g2s(smem_u32(ws.st[s].rp), p.Rp + tile * 288, 1152u, bar);
+        if (p.Rg) bulk_g2s(smem_u32(ws.st[s].rg), p.Rg + tile * 288, 1152u, bar);
+        if (p.gt_euler) bulk_g2s(smem_u32(ws.st[s].ge), p.gt_euler + tile * 96, 384u, bar);
+    };
+
+    long long tile = (long long)blockIdx.x * kMetWarps + warp;
+    if (lane == 0 && tile < full_tiles) fetch(tile, 0);
+    unsigned it = 0;
+    for (; tile < tiles; tile += stride, ++it) {
+        const int s = it & 1;
+        const long long next = tile + stride;
+        if (lane == 0 && next < full_tiles) fetch(next, s ^ 1);
+        MetStage& st = ws.st[s];
+        const long long base = tile * 32;
+        const int count = (int)min(32LL, p.n - base);
+        if (tile < full_tiles) {
+            mbar_wait(bar0 + 8u * s, (it >> 1) & 1u);
+        } else {
+            plain_tile(st.rp, p.Rp + base * 9, count * 9, lane);
+            if (p.Rg) plain_tile(st.rg, p.Rg + base * 9, count * 9, lane);
+            if (p.gt_euler) plain_tile(st.ge, p.gt_euler + base * 3, count * 3, lane);
+            __syncwarp();
+        }
+        if (lane < count) {
             float Rp[9], Rg[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) Rp[k] = sp[t * 9 + k];
-            const long long i = base + t;
+            for (int k = 0; k < 9; ++k) Rp[k] = st.rp[lane * 9 + k];
+            const long long i = base + lane;
             if (p.Rg) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) Rg[k] = sg[t * 9 + k];
+                for (int k = 0; k < 9; ++k) Rg[k] = st.rg[lane * 9 + k];
                 if (p.geo_deg || p.sums) {
                     bool ok;
                     const float g = geodesic_degrees(relative_trace(Rp, Rg), &ok);
@@ -84,41 +140,47 @@ metrics_kernel(MetricsArgs p, bool vec_ok) {
             if (want_euler) {
                 float e[3];
                 euler_from_rotation(Rp, p.full_range != 0, e);
-                so[t * 3] = e[0]; so[t * 3 + 1] = e[1]; so[t * 3 + 2] = e[2];
+                ws.eul[lane * 3] = e[0]; ws.eul[lane * 3 + 1] = e[1]; ws.eul[lane * 3 + 2] = e[2];
                 if (p.gt_euler) {
-                    float d[3], gt[3] = {se[t * 3], se[t * 3 + 1], se[t * 3 + 2]};
+                    float d[3], sum = 0.0f;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const float deg = div_rn(mul_rn(e[k], 180.0f), 3.14159265358979323846f);
-                        d[k] = fabsf(deg - gt[k]);
+                        d[k] = fabsf(rad_to_deg_ref(e[k]) - st.ge[lane * 3 + k]);
+                        sum = add_rn(sum, d[k]);
                         acc[2 + k] += (double)d[k];
                     }
-                    const float m = euler_mae_degrees(e, gt);
+                    const float m = div_by_const(sum, 3.0f, (float)(1.0 / 3.0));      // == euler_mae_degrees
                     if (p.mae) p.mae[i] = m;
                     acc[5] += (double)m;
-                    se[t * 3] = d[0]; se[t * 3 + 1] = d[1]; se[t * 3 + 2] = d[2];
+                    ws.err[lane * 3] = d[0]; ws.err[lane * 3 + 1] = d[1]; ws.err[lane * 3 + 2] = d[2];
                 }
             }
         }
-        __syncthreads();
-        if (p.euler) stage_out(p.euler + base * 3, so, count * 3, full);
-        if (p.abs_err && p.gt_euler) stage_out(p.abs_err + base * 3, se, count * 3, full);
-        __syncthreads();
+        __syncwarp();                      // stage s fully read (it is refilled next iteration); eul/err complete
+        if (p.euler || (p.abs_err && p.gt_euler)) {
+            if (vec_ok && count == 32) {
+                if (lane < 24) {
+                    if (p.euler) reinterpret_cast<float4*>(p.euler + base * 3)[lane] = reinterpret_cast<const float4*>(ws.eul)[lane];
+                    if (p.abs_err && p.gt_euler) reinterpret_cast<float4*>(p.abs_err + base * 3)[lane] = reinterpret_cast<const float4*>(ws.err)[lane];
+                }
+            } else {
+                for (int j = lane; j < count * 3; j += 32) {
+                    if (p.euler) p.euler[base * 3 + j] = ws.eul[j];
+                    if (p.abs_err && p.gt_euler) p.abs_err[base * 3 + j] = ws.err[j];
+                }
+            }
+            __syncwarp();
+        }
     }
     if (bad && p.status) atomicOr(p.status, kStatusTraceRange);
     if (p.sums) {
+        // warp sums, then one atomic per warp and quantity (148 x 32 warps: negligible)
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             double v = acc[k];
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
-            if ((t & 31) == 0) red[k][t >> 5] = v;
-        }
-        __syncthreads();
-        if (t < 6) {
-            double v = 0;
-            for (int w = 0; w < kMetThreads / 32; ++w) v += red[t][w];
-            atomicAdd(p.sums + t, v);
+            if (lane == 0 && v != 0.0) atomicAdd(p.sums + k, v);
         }
     }
 }
@@ -130,13 +192,17 @@ cudaError_t launch_metrics(MetricsArgs p, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (p.n + kMetThreads - 1) / kMetThreads;
-    long long blocks = tiles;
-    const long long cap = (long long)sms * 6;
+    constexpr size_t kSmem = sizeof(MetWarp) * kMetWarps;
+    static_assert(kSmem * kMetCtasPerSm <= 227 * 1024, "metrics_kernel: shared memory of the resident CTAs exceeds one SM");
+    cudaError_t err = cudaFuncSetAttribute(metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (err != cudaSuccess) return err;
+    const long long tiles = (p.n + 31) / 32;
+    long long blocks = (tiles + kMetWarps - 1) / kMetWarps;
+    const long long cap = (long long)sms * kMetCtasPerSm;        // persistent: every warp streams its share of tiles
     if (blocks > cap) blocks = cap;
     auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec_ok = al(p.Rp) && al(p.Rg) && al(p.gt_euler) && al(p.euler) && al(p.abs_err);
-    metrics_kernel<<<(unsigned)blocks, kMetThreads, 0, stream>>>(p, vec_ok);
+    metrics_kernel<<<(unsigned)blocks, kMetThreads, kSmem, stream>>>(p, vec_ok);
     return cudaGetLastError();
 }
 

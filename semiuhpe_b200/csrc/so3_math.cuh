@@ -658,33 +658,94 @@ SUHPE_HD float key_entropy(uint32_t k) {
 // ----------------------------------------------------------------------------
 // Error metrics.
 // ----------------------------------------------------------------------------
+SUHPE_HD float mufu_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// a / b for a compile-time constant b with y = RN(1/b): q = a y, r = a - b q (exact in the FMA),
+// q' = q + r y (Markstein).  Checked exhaustively on the host against IEEE division for EVERY
+// float with 1e-30 <= |a| <= 1e30, for b = fl(pi) and b = 3 (the two divisors of
+// src/agent.py:452-454): bit-identical.  Three FMA-pipe instructions instead of the ~10 + slow
+// path of __fdiv_rn.
+SUHPE_HD float div_by_const(float a, float b, float y) {
+    const float q = mul_rn(a, y);
+    const float r = fmaf(-b, q, a);
+    return fmaf(r, y, q);
+}
+constexpr float kPiF = 3.14159265358979323846f;
+SUHPE_HD float rad_to_deg_ref(float rad) {          // euler * 180 / np.pi in fp32, two roundings like torch
+    return div_by_const(mul_rn(rad, 180.0f), kPiF, (float)(1.0 / (double)kPiF));
+}
+
+// atan2(y, x), branch-free: t = min/max in [0,1] by MUFU.RCP + one Newton step, atan(t) =
+// t + t s P7(s), s = t^2 (weighted minimax fit, |rel err| < 0.3 * 2^-24 before rounding), then
+// the octant is unfolded with two-term pi/2 and pi.  Measured against double atan2 on 10^7 random
+// rotation entries and the axis / signed-zero cases: <= 2 ulp (tests/test_emul_math.py).  IEEE
+// behaviour kept for signed zeros and x = y = 0; infinities are not handled (rotation entries).
+SUHPE_HD float atan2_so3(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    // keep 1/mx a normal number over the whole exponent range
+    const float sc = (mx < 1e-30f) ? 1.8446744e19f : ((mx > 1e30f) ? 5.4210109e-20f : 1.0f);   // 2^64, 2^-64
+    mx *= sc; mn *= sc;
+    const float r = mufu_rcp(mx);
+    float t = mn * r;
+    t = fmaf(fmaf(-t, mx, mn), r, t);
+    t = (mx > 0.0f) ? t : 0.0f;                                  // atan2(+-0, +-0)
+    const float s = t * t;
+    float p = 0.0029504755854872678f;
+    p = fmaf(p, s, -0.01648717905513075f);
+    p = fmaf(p, s, 0.043405680097467356f);
+    p = fmaf(p, s, -0.07568590190914992f);
+    p = fmaf(p, s, 0.10673642075124151f);
+    p = fmaf(p, s, -0.1421297326642285f);
+    p = fmaf(p, s, 0.19994003814484457f);
+    p = fmaf(p, s, -0.33333162357779944f);
+    float a = fmaf(p * s, t, t);
+    if (ay > ax) a = (1.57079637050628662109375f - a) + -4.37113882867379e-8f;       // pi/2 = hi + lo
+#if defined(__CUDA_ARCH__)
+    const bool xneg = __float_as_int(x) < 0;
+#else
+    const bool xneg = signbit(x);
+#endif
+    if (xneg) a = (3.1415927410125732421875f - a) + -8.74227765734758e-8f;           // pi = hi + lo
+    a = copysignf(a, y);
+    return (x != x || y != y) ? x + y : a;
+}
+
 // (pitch, yaw, roll) in radians, src/utils.py:232-260 incl. the arithmetic blend
-// with the singular flag taken before the full-range flip.
+// with the singular flag taken before the full-range flip.  The singular branch (xs) is only
+// evaluated where the flag is set: x*1 + xs*0 == x exactly for every finite xs.
 SUHPE_HD void euler_from_rotation(const float* R, bool full_range, float* out) {
     const float r00 = R[0], r10 = R[3];
     float sy = sqrt_rn(add_rn(mul_rn(r00, r00), mul_rn(r10, r10)));
-    const float sing = (sy < 1e-6f) ? 1.0f : 0.0f;
+    const bool singular = sy < 1e-6f;
     if (full_range && r00 < 0.0f) sy = -sy;
-    const float x = atan2f(R[7], R[8]);
-    const float y = atan2f(-R[6], sy);
-    const float z = atan2f(r10, r00);
-    const float xs = atan2f(-R[5], R[4]);
-    const float zs = r10 * 0.0f;
-    const float keep = 1.0f - sing;
-    out[0] = add_rn(mul_rn(x, keep), mul_rn(xs, sing));
-    out[1] = add_rn(mul_rn(y, keep), mul_rn(y, sing));
-    out[2] = add_rn(mul_rn(z, keep), mul_rn(zs, sing));
+    const float x = atan2_so3(R[7], R[8]);
+    const float y = atan2_so3(-R[6], sy);
+    const float z = atan2_so3(r10, r00);
+    out[0] = x; out[1] = y; out[2] = z;
+    if (singular) {
+        const float xs = atan2_so3(-R[5], R[4]);
+        const float zs = r10 * 0.0f;
+        out[0] = add_rn(mul_rn(x, 0.0f), mul_rn(xs, 1.0f));
+        out[1] = add_rn(mul_rn(y, 0.0f), mul_rn(y, 1.0f));
+        out[2] = add_rn(mul_rn(z, 0.0f), mul_rn(zs, 1.0f));
+    }
 }
 
 // mean_3 | euler * 180 / pi - gt_euler_deg |   (src/agent.py:452-454)
 SUHPE_HD float euler_mae_degrees(const float* euler_rad, const float* gt_deg) {
     float acc = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float deg = div_rn(mul_rn(euler_rad[k], 180.0f), 3.14159265358979323846f);
-        acc = add_rn(acc, fabsf(deg - gt_deg[k]));
-    }
-    return div_rn(acc, 3.0f);
+    for (int k = 0; k < 3; ++k) acc = add_rn(acc, fabsf(rad_to_deg_ref(euler_rad[k]) - gt_deg[k]));
+    return div_by_const(acc, 3.0f, (float)(1.0 / 3.0));
 }
 
 // trace(Rp Rg^T) = sum_ij Rp_ij Rg_ij

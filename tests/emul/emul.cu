@@ -220,6 +220,13 @@ void emul_metrics(const float* Rp, const float* Rg, const float* gt_euler, long 
     }
 }
 
+void emul_atan2(const float* y, const float* x, long n, float* out) {
+    for (long i = 0; i < n; ++i) out[i] = atan2_so3(y[i], x[i]);
+}
+
+void emul_rad_to_deg(const float* rad, long n, float* out) {
+    for (long i = 0; i < n; ++i) out[i] = rad_to_deg_ref(rad[i]);
+}
 
 // K2L with the kernel's two decompositions: L = 1 (one thread walks the grid in order) and
 // L = 32 (lane l takes points l, l+32, ...; partials rebased to the common minimum, butterfly-merged)

@@ -203,3 +203,45 @@ def test_run_boundaries_are_exact(emul):
     # the flat pass-item list the warp replays covers every kept node exactly once, with the right type
     for bits in (0, 26):
         assert emul.emul_check_items(P(S[:60000]), ctypes.c_long(60000), ctypes.c_int(bits)) == 0
+
+
+def ulp_err(got, exact64):
+    ulp = np.spacing(np.abs(exact64).astype(np.float32)).astype(np.float64)
+    return np.abs(got.astype(np.float64) - exact64) / ulp
+
+
+def test_atan2_accuracy_and_special_cases(emul):
+    """K4's branch-free atan2 (so3_math.cuh): <= 2 ulp against double atan2 on rotation-like
+    arguments of every octant and magnitude, IEEE results on the axes and for signed zeros."""
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    y = rng.uniform(-1, 1, n).astype(np.float32)
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    scale = (10.0 ** rng.uniform(-37, 37, n)).astype(np.float32)      # ratio is what matters
+    y[n // 2:] *= scale[n // 2:]; x[n // 2:] *= scale[n // 2:]
+    tiny = (10.0 ** rng.uniform(-9, 0, n // 4)).astype(np.float32)    # near-axis angles
+    y[:n // 4] *= tiny
+    out = np.zeros(n, np.float32)
+    emul.emul_atan2(P(y), P(x), ctypes.c_long(n), P(out))
+    exact = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    ok = np.isfinite(y) & np.isfinite(x) & (np.abs(exact) > 1e-36)
+    assert ulp_err(out[ok], exact[ok]).max() <= 2.0
+    ys = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, -0.0, 1.0, 1.0, np.nan, 1.0, 1e-30, 3e-39], np.float32)
+    xs = np.array([1.0, 1.0, -1.0, -1.0, 0.0, 0.0, 0.0, -0.0, -0.0, 1.0, 1.0, np.nan, -1e-30, 1e-39], np.float32)
+    got = np.zeros(len(ys), np.float32)
+    emul.emul_atan2(P(ys), P(xs), ctypes.c_long(len(ys)), P(got))
+    want = np.arctan2(ys, xs)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    fin = ~np.isnan(want)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=3e-7, atol=0)
+    np.testing.assert_array_equal(np.signbit(got[fin]), np.signbit(want[fin]))
+
+
+def test_degrees_conversion_is_the_reference_rounding(emul):
+    """euler*180/np.pi in fp32 (two roundings, src/agent.py:452): the Markstein form is bit-identical."""
+    rng = np.random.default_rng(1)
+    rad = np.concatenate([rng.uniform(-np.pi, np.pi, 2_000_000), [0.0, np.pi, -np.pi, 1e-20, 1e-7]]).astype(np.float32)
+    out = np.zeros_like(rad)
+    emul.emul_rad_to_deg(P(rad), ctypes.c_long(len(rad)), P(out))
+    ref = (torch.from_numpy(rad) * 180 / np.pi).numpy()
+    np.testing.assert_array_equal(out, ref)
