@@ -23,6 +23,7 @@
 // Per-sample set-up (proper SVD, T, the ground-truth term) runs in fp64: see laplace_setup.
 #include "kernels.cuh"
 #include "so3_math.cuh"
+#include <stdlib.h>
 
 namespace suhpe {
 
@@ -42,10 +43,14 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 dup(float x) { return pk(x, x); }
 
 constexpr int kStreamThreads = 512;
-constexpr int kStreamChunk = 6144;         // grid points per shared-memory chunk (216 KB), multiple of 4
 
 // block sums of the packed loop: lo half = even grid points, hi half = odd
 struct PackedSums { f2 z, c, m[9]; };
+
+// accumulate in place: pins every accumulator to one register pair for the whole loop (without
+// this the compiler renames them across the unrolled pairs and copies 18 registers back per trip)
+__device__ __forceinline__ void acc_add2(f2& acc, f2 y) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(y)); }
+__device__ __forceinline__ void acc_fma2(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 
 __device__ __forceinline__ void packed_scale(PackedSums& s, float sc) {
     const f2 k = dup(sc);
@@ -54,52 +59,71 @@ __device__ __forceinline__ void packed_scale(PackedSums& s, float sc) {
     for (int i = 0; i < 9; ++i) s.m[i] = mul2(s.m[i], k);
 }
 
-// two grid points (r[i] = (R_k[i], R_k+1[i])) in one straight-line FFMA2 body; same arithmetic per
-// point as laplace_accum_point
-__device__ __forceinline__ void packed_pair(LaplaceAccum& a, PackedSums& s, const float* A, float T, const f2* r) {
+// One pair of grid points, first half: nq = -q = -sqrt(max(T - <A,R_k>, eps)) for both points and
+// rs = 1/q, live = (d >= eps).  Everything is carried NEGATED (nd = t - T, nq = nd * rs), which
+// makes the Newton step and the exponent plain FFMA2s with no sign flips:
+//   ne = nq*nq + nd = q^2 - d,   nq' = nq + (rs/2) ne,   exponent = (qmin - q) log2e = nq' log2e + qmin log2e
+// Same arithmetic per point as laplace_accum_point / sqrt_pair (negation is exact).
+struct PairRoots { f2 nq, rs; bool live0, live1; };
+
+__device__ __forceinline__ PairRoots packed_roots(const float* A, float T, const f2* r) {
     f2 t = mul2(dup(A[0]), r[0]);
 #pragma unroll
     for (int i = 1; i < 9; ++i) t = fma2(dup(A[i]), r[i], t);
-    float d0, d1;
-    upk(fma2(t, dup(-1.0f), dup(T)), d0, d1);
-    const bool live0 = d0 >= kLapEps, live1 = d1 >= kLapEps;
-    d0 = fmaxf(d0, kLapEps); d1 = fmaxf(d1, kLapEps);
-    const f2 d = pk(d0, d1), rs = pk(mufu_rsqrt(d0), mufu_rsqrt(d1));
-    f2 q = mul2(d, rs);
-    q = fma2(mul2(rs, dup(0.5f)), fma2(mul2(q, dup(-1.0f)), q, d), q);
-    float q0, q1;
-    upk(q, q0, q1);
-    const float qm = fminf(q0, q1);
-    if (qm < a.qmin) {                        // new running maximum of p = -q: rescale (rare)
-        const float sc = mufu_ex2((qm - a.qmin) * kLog2e);
-        laplace_accum_scale(a, sc);
-        packed_scale(s, sc);
-        a.qmin = qm;
-    }
+    float n0, n1;
+    upk(add2(t, dup(-T)), n0, n1);                             // nd = <A,R_k> - T
+    PairRoots o;
+    o.live0 = n0 <= -kLapEps; o.live1 = n1 <= -kLapEps;        // clamp_min passes the gradient where input >= min
+    n0 = fminf(n0, -kLapEps); n1 = fminf(n1, -kLapEps);
+    const f2 nd = pk(n0, n1);
+    o.rs = pk(mufu_rsqrt(-n0), mufu_rsqrt(-n1));
+    const f2 nq = mul2(nd, o.rs);
+    o.nq = fma2(mul2(o.rs, dup(0.5f)), fma2(nq, nq, nd), nq);
+    return o;
+}
+
+// second half: weights and sums, relative to the running minimum held as qminL = qmin * log2e
+__device__ __forceinline__ void packed_sums(PackedSums& s, const PairRoots& o, float qminL, const f2* r) {
     float e0, e1;
-    upk(fma2(q, dup(-kLog2e), dup(a.qmin * kLog2e)), e0, e1);
-    const f2 w = mul2(pk(mufu_ex2(e0), mufu_ex2(e1)), rs);    // exp(p - c) / (-p)
-    s.z = add2(s.z, w);
+    upk(fma2(o.nq, dup(kLog2e), dup(qminL)), e0, e1);
+    const f2 w = mul2(pk(mufu_ex2(e0), mufu_ex2(e1)), o.rs);   // exp(p - c) / (-p)
+    acc_add2(s.z, w);
     float c0, c1;
-    upk(mul2(w, fma2(rs, rs, rs)), c0, c1);                    // w (1/q + 1/q^2)
-    const f2 cw = pk(live0 ? c0 : 0.0f, live1 ? c1 : 0.0f);
-    s.c = add2(s.c, cw);
+    upk(mul2(w, fma2(o.rs, o.rs, o.rs)), c0, c1);               // w (1/q + 1/q^2)
+    const f2 cw = pk(o.live0 ? c0 : 0.0f, o.live1 ? c1 : 0.0f);
+    acc_add2(s.c, cw);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) s.m[i] = fma2(cw, r[i], s.m[i]);
+    for (int i = 0; i < 9; ++i) acc_fma2(s.m[i], cw, r[i]);
 }
 
-__device__ __forceinline__ void packed_flush(LaplaceAccum& a, PackedSums& s) {
+// Per-thread state that is touched once per 128 grid points (or once per sample) is parked in
+// shared memory behind the grid, [slot][thread], so the hot loop keeps its registers for the 22
+// packed block sums and the grid operands:
+//   slots 0-10  totals Z, C, M[9], expressed relative to slot 11 = the running minimum they were
+//               last folded at (the block sums are relative to the CURRENT minimum; the fold rescales)
+//   slots 12-20 mode R*,  slots 21-22 the fp64 trace T
+constexpr int kParkSlots = 23;
+constexpr int kStreamChunk = ((227 * 1024 - kParkSlots * kStreamThreads * 4) / 36) & ~3;   // grid points per smem chunk
+
+__device__ __forceinline__ void park_fold(float* park, PackedSums& s, float qmin) {
+    const float sc = mufu_ex2((qmin - park[11 * kStreamThreads]) * kLog2e);    // first fold: 2^-inf = 0
     float lo, hi;
-    upk(s.z, lo, hi); a.z += lo + hi; s.z = pk(0.f, 0.f);
-    upk(s.c, lo, hi); a.c += lo + hi; s.c = pk(0.f, 0.f);
+    upk(s.z, lo, hi); park[0] = fmaf(park[0], sc, lo + hi); s.z = pk(0.f, 0.f);
+    upk(s.c, lo, hi); park[kStreamThreads] = fmaf(park[kStreamThreads], sc, lo + hi); s.c = pk(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { upk(s.m[i], lo, hi); a.m[i] += lo + hi; s.m[i] = pk(0.f, 0.f); }
-    laplace_accum_flush(a);
+    for (int i = 0; i < 9; ++i) {
+        upk(s.m[i], lo, hi);
+        park[(2 + i) * kStreamThreads] = fmaf(park[(2 + i) * kStreamThreads], sc, lo + hi);
+        s.m[i] = pk(0.f, 0.f);
+    }
+    park[11 * kStreamThreads] = qmin;
 }
 
+template <int UNROLL>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 laplace_stream_kernel(LaplaceArgs p, int chunk) {
     extern __shared__ __align__(16) float gp[];      // [chunk/2][9][2]: point pairs interleaved per component
+    float* park = gp + (size_t)chunk * 9 + threadIdx.x;
     const long long tiles = (p.n + kStreamThreads - 1) / kStreamThreads;
     const bool single_chunk = p.N <= chunk;
     bool bad = false;
@@ -116,15 +140,24 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long sample = tile * kStreamThreads + threadIdx.x;
         const bool valid = sample < p.n;
-        float A[9], Rs[9];
-        double Td;
+        float A[9], T;
+        {
+            float Rs[9];
+            double Td;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) A[i] = valid ? __ldg(p.A + sample * 9 + i) : ((i % 4 == 0) ? 1.f : 0.f);
-        if (!laplace_setup(A, Rs, &Td) && valid) bad = true;
-        const float T = (float)Td;
+            for (int i = 0; i < 9; ++i) A[i] = valid ? __ldg(p.A + sample * 9 + i) : ((i % 4 == 0) ? 1.f : 0.f);
+            if (!laplace_setup(A, Rs, &Td) && valid) bad = true;
+            T = (float)Td;
+#pragma unroll
+            for (int i = 0; i < 11; ++i) park[i * kStreamThreads] = 0.f;
+            park[11 * kStreamThreads] = INFINITY;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) park[(12 + i) * kStreamThreads] = Rs[i];
+            park[21 * kStreamThreads] = __int_as_float(__double2loint(Td));
+            park[22 * kStreamThreads] = __int_as_float(__double2hiint(Td));
+        }
 
-        LaplaceAccum a;
-        laplace_accum_init(a);
+        float qmin = INFINITY, qminL = INFINITY;              // running minimum of q and qmin * log2e
         PackedSums s;
         s.z = s.c = pk(0.f, 0.f);
 #pragma unroll
@@ -137,7 +170,7 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
             const float4* g4 = reinterpret_cast<const float4*>(gp);
             for (int g0 = 0; g0 < groups; g0 += 32) {         // fold into the totals every 128 points
                 const int g1 = min(g0 + 32, groups);
-#pragma unroll 1
+#pragma unroll UNROLL
                 for (int g = g0; g < g1; ++g) {
                     f2 r[18];
 #pragma unroll
@@ -145,22 +178,49 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
                         const float4 x = g4[g * 9 + v];
                         r[2 * v] = pk(x.x, x.y); r[2 * v + 1] = pk(x.z, x.w);
                     }
-                    packed_pair(a, s, A, T, r);
-                    packed_pair(a, s, A, T, r + 9);
+                    // roots of all four points first, ONE running-minimum check per group (the
+                    // rescale is rare), then the weights: the two pairs are independent
+                    // straight-line chains the scheduler can interleave
+                    const PairRoots o0 = packed_roots(A, T, r);
+                    const PairRoots o1 = packed_roots(A, T, r + 9);
+                    float a0, a1, b0, b1;
+                    upk(o0.nq, a0, a1); upk(o1.nq, b0, b1);
+                    const float qm = -fmaxf(fmaxf(a0, a1), fmaxf(b0, b1));
+                    if (qm < qmin) {                          // new running maximum of p = -q
+                        packed_scale(s, mufu_ex2((qm - qmin) * kLog2e));
+                        qmin = qm;
+                        qminL = qm * kLog2e;
+                    }
+                    packed_sums(s, o0, qminL, r);
+                    packed_sums(s, o1, qminL, r + 9);
                 }
-                packed_flush(a, s);
+                park_fold(park, s, qmin);
             }
-            for (int k = groups * 4; k < cn; ++k) {           // up to 3 trailing points
-                float r[9];
+            if (groups * 4 < cn) {                            // up to 3 trailing points: scalar path, then merged
+                LaplaceAccum ta;
+                laplace_accum_init(ta);
+                for (int k = groups * 4; k < cn; ++k) {
+                    float r[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) r[i] = gp[(k >> 1) * 18 + 2 * i + (k & 1)];
-                laplace_accum_point(a, A, T, r);
+                    for (int i = 0; i < 9; ++i) r[i] = gp[(k >> 1) * 18 + 2 * i + (k & 1)];
+                    laplace_accum_point(ta, A, T, r);
+                }
+                if (ta.qmin < qmin) qmin = ta.qmin; else laplace_accum_scale(ta, mufu_ex2((qmin - ta.qmin) * kLog2e));
+                qminL = qmin * kLog2e;
+                s.z = pk(ta.z, 0.f); s.c = pk(ta.c, 0.f);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) s.m[i] = pk(ta.m[i], 0.f);
+                park_fold(park, s, qmin);
             }
-            laplace_accum_flush(a);
         }
 
         if (valid) {
-            float Rg[9], grad[9], nll, logF;
+            float Rg[9], Rs[9], grad[9], nll, logF;
+            LaplaceAccum a;
+            a.qmin = qmin; a.Z = park[0]; a.C = park[kStreamThreads];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { a.M[i] = park[(2 + i) * kStreamThreads]; Rs[i] = park[(12 + i) * kStreamThreads]; }
+            const double Td = __hiloint2double(__float_as_int(park[22 * kStreamThreads]), __float_as_int(park[21 * kStreamThreads]));
 #pragma unroll
             for (int i = 0; i < 9; ++i) Rg[i] = __ldg(p.Rgt + sample * 9 + i);
             laplace_finish(a, laplace_gt_gap(A, Rg, Td), Rs, Rg, p.N, &nll, &logF, grad);
@@ -286,12 +346,19 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     cudaError_t err;
     if (per_thread) {
         const int chunk = p.N < kStreamChunk ? ((p.N + 3) & ~3) : kStreamChunk;
-        const size_t smem = (size_t)chunk * 9 * sizeof(float);
-        err = cudaFuncSetAttribute(laplace_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
+        const size_t smem = ((size_t)chunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);
+        static const int unroll = [] { const char* e = getenv("SUHPE_LAP_UNROLL"); return e ? atoi(e) : 1; }();   // A/B knob
         const long long tiles = (p.n + kStreamThreads - 1) / kStreamThreads;
         const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
-        laplace_stream_kernel<<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
+        if (unroll == 2) {
+            err = cudaFuncSetAttribute(laplace_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+            laplace_stream_kernel<2><<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
+        } else {
+            err = cudaFuncSetAttribute(laplace_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+            laplace_stream_kernel<1><<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
+        }
     } else {
         const int chunk = p.N < kGridChunk ? p.N : kGridChunk;
         const int stride = (chunk + 3) & ~3;
