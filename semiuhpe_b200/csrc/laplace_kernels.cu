@@ -23,7 +23,6 @@
 // Per-sample set-up (proper SVD, T, the ground-truth term) runs in fp64: see laplace_setup.
 #include "kernels.cuh"
 #include "so3_math.cuh"
-#include <stdlib.h>
 
 namespace suhpe {
 
@@ -119,7 +118,6 @@ __device__ __forceinline__ void park_fold(float* park, PackedSums& s, float qmin
     park[11 * kStreamThreads] = qmin;
 }
 
-template <int UNROLL>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 laplace_stream_kernel(LaplaceArgs p, int chunk) {
     extern __shared__ __align__(16) float gp[];      // [chunk/2][9][2]: point pairs interleaved per component
@@ -170,7 +168,7 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
             const float4* g4 = reinterpret_cast<const float4*>(gp);
             for (int g0 = 0; g0 < groups; g0 += 32) {         // fold into the totals every 128 points
                 const int g1 = min(g0 + 32, groups);
-#pragma unroll UNROLL
+#pragma unroll 1
                 for (int g = g0; g < g1; ++g) {
                     f2 r[18];
 #pragma unroll
@@ -347,18 +345,11 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     if (per_thread) {
         const int chunk = p.N < kStreamChunk ? ((p.N + 3) & ~3) : kStreamChunk;
         const size_t smem = ((size_t)chunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);
-        static const int unroll = [] { const char* e = getenv("SUHPE_LAP_UNROLL"); return e ? atoi(e) : 1; }();   // A/B knob
+        err = cudaFuncSetAttribute(laplace_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
         const long long tiles = (p.n + kStreamThreads - 1) / kStreamThreads;
-        const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
-        if (unroll == 2) {
-            err = cudaFuncSetAttribute(laplace_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (err != cudaSuccess) return err;
-            laplace_stream_kernel<2><<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
-        } else {
-            err = cudaFuncSetAttribute(laplace_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (err != cudaSuccess) return err;
-            laplace_stream_kernel<1><<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
-        }
+        const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);    // one persistent CTA per SM
+        laplace_stream_kernel<<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
     } else {
         const int chunk = p.N < kGridChunk ? p.N : kGridChunk;
         const int stride = (chunk + 3) & ~3;
