@@ -30,6 +30,7 @@ extern "C" {
 /* bits OR-ed into the optional device `status` word */
 #define SUHPE_STATUS_NONFINITE   1  /* A held NaN/Inf: torch.svd raises there (fisher_utils.py:28) */
 #define SUHPE_STATUS_TRACE_RANGE 2  /* trace(R1 R2^T) out of [-1-1e-4, 3+1e-4]: pytorch3d raises ValueError */
+#define SUHPE_STATUS_NONFINITE_CE 4 /* a cross entropy is NaN/Inf: the reference asserts (fisher_utils.py:98) */
 
 #define SUHPE_HIST_BINS 2048        /* uint64 counters per radix histogram */
 #define SUHPE_SELECT_STATE_BYTES 32 /* opaque device block, see suhpe_select_read */
@@ -64,6 +65,18 @@ int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float ov
  * that provably negligible prefix.  Default 26 (a quarter of an fp32 ulp of the sum: below what
  * the reference's own fp32 torch.sum resolves); 0 evaluates all 512 nodes of every integral. */
 int suhpe_set_quadrature_cut_bits(int bits);
+
+/* fisher_CE(A1 = target, A2 = prediction) -> ce (n) and d ce_i / d A2_i (n,9, nullable): the
+ * cross entropy of two matrix-Fisher densities through their Bingham forms, the reference's default
+ * unsupervised loss (src/fisher/fisher_utils.py:84-99 -> between_bingham_fisher.py:107-152 ->
+ * bingham_utils.py:5-32, reproduced with its row/column quirk at bingham_utils.py:27).  Two K2
+ * launches (the quadratures of A1 and A2) and one closing kernel that evaluates the value and
+ * the gradient in closed form (what autograd yields through torch.svd, matrix_to_quaternion and
+ * the logC_F backward).  A1 is a constant (the agent detaches the teacher: src/agent.py:107).
+ * workspace: SUHPE_FISHER_CE_WORKSPACE_FLOATS * n floats of device scratch, caller-owned. */
+#define SUHPE_FISHER_CE_WORKSPACE_FLOATS 10
+int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
+                        float* workspace, int* status, void* stream);
 
 /* K2 on given singular values: logC_F(S) and its backward G = dlogC/dS, entropy(S)
  * (src/fisher/torch_norm_factor.py:66-92 `logC_F`; S (n,3) sorted s1>=s2>=|s3| like every

@@ -257,6 +257,165 @@ def fisher_entropy_closed_form(A):
     return torch.log(half) + (s * (1 - g)).sum(1)
 
 
+# ------------------------------------------------------------------- f1
+def fisher_to_bingham_frame(A, dtype_eye=None):
+    """Quaternion frame V (b,4,4) and Fisher-convention Lambda (b,4) of a matrix-Fisher
+    parameter (src/fisher/between_bingham_fisher.py:107-135): columns are the quaternions
+    of U E_k V^T (E_k = 2 e_k e_k^T - I) and of U V^T."""
+    u, s, v = proper_svd(A)
+    s1, s2, s3 = s[:, 0], s[:, 1], s[:, 2]
+    l1 = s1 - s2 - s3
+    l2 = s2 - s1 - s3
+    l3 = s3 - s1 - s2
+    l4 = -l1 - l2 - l3
+    lam = torch.stack((l1, l2, l3, l4), 1)
+    eye = torch.eye(3, dtype=A.dtype)
+    cols = []
+    for k in range(4):
+        if k < 3:
+            e = torch.zeros(3, 1, dtype=A.dtype)
+            e[k] += 1
+            E = 2 * (e @ e.t()) - eye
+        else:
+            E = eye
+        cols.append(p3d.matrix_to_quaternion(u @ E[None] @ v.transpose(1, 2)))
+    return torch.stack(cols, 2), lam
+
+
+def to_bingham_convention(V, lam):
+    """Shift so the largest Lambda is 0, sort descending, permute the frame's columns alike
+    (src/fisher/between_bingham_fisher.py:138-152)."""
+    lam = lam + (-lam.max(1)[0]).unsqueeze(-1)
+    lam, order = lam.sort(descending=True)
+    V = torch.gather(V, -1, order[:, None, :].repeat(1, V.shape[1], 1))
+    return V, lam
+
+
+def _bingham_dF(lam3):
+    """dF/dLam of the last three Bingham parameters (src/fisher/bingham_utils.py:59-73)."""
+    full = torch.cat((torch.zeros_like(lam3[:, :1]), lam3), -1)
+    with torch.enable_grad():
+        leaf = full.detach().requires_grad_(True)
+        F = _bingham_F(leaf)
+        dF = torch.autograd.grad(F, leaf, torch.ones_like(F))[0]
+    return dF[:, 1:]
+
+
+def bingham_cross_entropy(VB1, lamB1, VB2, lamB2):
+    """h(f1, f2), f1 the target (src/fisher/bingham_utils.py:5-32), bug-for-bug:
+    ``LamB1.argmax()`` is a flattened argmax (0, because element [0,0] = 0 is the maximum) used
+    as a column index, and ``A[:, i]`` takes ROW i of V1^T V2 where the expectation
+    E_1[(v2_i . q)^2] would need column i."""
+    mu = VB1[:, :, int(lamB1.argmax())]
+    VB1, VB2 = VB1[..., 1:], VB2[..., 1:]
+    lamB1, lamB2 = lamB1[..., 1:], lamB2[..., 1:]
+    pad = lambda l: torch.cat((torch.zeros_like(l[:, :1]), l), -1)
+    first = torch.log(_bingham_F(pad(lamB2)))
+    second = 0
+    A = VB1.transpose(1, 2) @ VB2
+    b = (mu[:, None, :] @ VB2).squeeze(1)
+    F1 = _bingham_F(pad(lamB1))
+    dF1 = _bingham_dF(lamB1)
+    for i in range(3):
+        tmp = (A[:, i] ** 2 - b[:, i][:, None] ** 2) * (1 / F1[:, None]) * dF1
+        second = second + lamB2[:, i] * (b[:, i] ** 2 + tmp.sum(1))
+    return first - second
+
+
+def fisher_ce(A1, A2):
+    """Cross entropy of two matrix-Fisher densities through their Bingham forms, A1 the
+    target, A2 the prediction (src/fisher/fisher_utils.py:84-99); differentiable in A2
+    through torch.svd, the quaternion frame and the quadrature's custom backward."""
+    A1 = A1.reshape(-1, 3, 3)
+    A2 = A2.reshape(-1, 3, 3)
+    V1, lam1 = fisher_to_bingham_frame(A1)
+    V2, lam2 = fisher_to_bingham_frame(A2)
+    VB1, lamB1 = to_bingham_convention(V1, lam1)
+    VB2, lamB2 = to_bingham_convention(V2, lam2)
+    ce = bingham_cross_entropy(VB1, lamB1, VB2, lamB2)
+    return ce - torch.tensor([np.log(2 * np.pi ** 2)], dtype=ce.dtype)
+
+
+def _quat_of_rotation(R):
+    return p3d.matrix_to_quaternion(R)
+
+
+def _polar_rotation(p, q):
+    """Symmetric bilinear form of the homogeneous quaternion -> rotation map:
+    R~(q, q) = |q|^2 R(q);  x^T K(A) y = <A, R~(x, y)>."""
+    pw, px, py, pz = p.unbind(-1)
+    qw, qx, qy, qz = q.unbind(-1)
+    d = lambda a, b, c, e: a * c + b * e          # helper: a*c + b*e
+    r00 = pw * qw + px * qx - py * qy - pz * qz
+    r11 = pw * qw - px * qx + py * qy - pz * qz
+    r22 = pw * qw - px * qx - py * qy + pz * qz
+    xy = px * qy + py * qx
+    xz = px * qz + pz * qx
+    yz = py * qz + pz * qy
+    wx = pw * qx + px * qw
+    wy = pw * qy + py * qw
+    wz = pw * qz + pz * qw
+    return torch.stack((r00, xy - wz, xz + wy, xy + wz, r11, yz - wx, xz - wy, yz + wx, r22), -1).reshape(p.shape[:-1] + (3, 3))
+
+
+def fisher_ce_closed_form(A1, A2):
+    """The value of :func:`fisher_ce` and its gradient w.r.t. A2 without autograd (the form the
+    CUDA kernel evaluates; derivation in DESIGN.md).  With (U,s,V) the proper SVDs, g = grad logC,
+    the frames VB = [q(U V^T), q(U E_1 V^T), q(U E_2 V^T), q(U E_3 V^T)], W = VB1^T VB2,
+    gamma = expected squared projections of f1 (gamma_0 + ... + gamma_3 = 1) and
+    LamB2 = -2 (s2+s3, s1+s3, s1+s2) of A2:
+        CE = log f(s_2) - sum_{i=1..3} LamB2_i [ gamma_0 W_0i^2 + sum_{j=1..3} gamma_j W_ij^2 ]
+    The gradient uses first-order perturbation of the eigenpairs (lam_c, v_c) of the 4x4 matrix
+    K(A2) (x^T K(A) x = <A, R(x)> is linear in A):  dCE/dA2 = sum_kc G_kc R~(v_k, v_c)."""
+    A1 = A1.reshape(-1, 3, 3)
+    A2 = A2.reshape(-1, 3, 3)
+    b = A1.shape[0]
+    u1, s1, v1 = proper_svd(A1)
+    u2, s2, v2 = proper_svd(A2)
+    _, g1 = log_normaliser_grad(s1)
+    half2, g2 = log_normaliser_grad(s2)
+
+    def frame(u, v):
+        cols = [_quat_of_rotation(u @ v.transpose(1, 2))]
+        for k in range(3):
+            E = -torch.eye(3, dtype=u.dtype)
+            E[k, k] = 1
+            cols.append(_quat_of_rotation(u @ E[None] @ v.transpose(1, 2)))
+        return torch.stack(cols, 2)                          # (b,4,4), column c = v_c
+
+    VB1, VB2 = frame(u1, v1), frame(u2, v2)
+    W = VB1.transpose(1, 2) @ VB2                            # W[r][c] = v1_r . v2_c
+    gam = torch.stack((1 + g1[:, 0] + g1[:, 1] + g1[:, 2], 1 + g1[:, 0] - g1[:, 1] - g1[:, 2],
+                       1 - g1[:, 0] + g1[:, 1] - g1[:, 2], 1 - g1[:, 0] - g1[:, 1] + g1[:, 2]), 1) / 4
+    lamB = torch.stack((torch.zeros_like(s2[:, 0]), -2 * (s2[:, 1] + s2[:, 2]), -2 * (s2[:, 0] + s2[:, 2]),
+                        -2 * (s2[:, 0] + s2[:, 1])), 1)
+    W2 = W * W
+    phi = gam[:, :1] * W2[:, 0, :] + torch.einsum('bj,bij->bi', gam[:, 1:], W2[:, :, 1:])   # phi_i, i = 0..3 (0 unused)
+    ce = torch.log(half2) - (lamB[:, 1:] * phi[:, 1:]).sum(1)
+
+    # eigenvalues of K(A2) in frame order and d s / d lam
+    lam = torch.stack((s2.sum(1), s2[:, 0] - s2[:, 1] - s2[:, 2], -s2[:, 0] + s2[:, 1] - s2[:, 2],
+                       -s2[:, 0] - s2[:, 1] + s2[:, 2]), 1)
+    ds = torch.tensor([[1, 1, -1, -1], [1, -1, 1, -1], [1, -1, -1, 1]], dtype=A2.dtype) / 4   # ds_m / dlam_c
+    L_lam = (g2 - 1) @ ds                                    # log f part
+    L_lam[:, 1:] -= phi[:, 1:]
+    L_lam[:, 0] += phi[:, 1:].sum(1)
+    # D[k][c] = v2_k . d(second)/d v2_c   (c = 1..3)
+    D = torch.zeros(b, 4, 4, dtype=A2.dtype)
+    for c in range(1, 4):
+        for k in range(4):
+            D[:, k, c] = 2 * gam[:, 0] * lamB[:, c] * W[:, 0, c] * W[:, 0, k] \
+                + 2 * gam[:, c] * (lamB[:, 1:] * W[:, 1:, c] * W[:, 1:, k]).sum(1)
+    grad = torch.zeros_like(A2)
+    for c in range(4):
+        grad = grad + L_lam[:, c, None, None] * _polar_rotation(VB2[:, :, c], VB2[:, :, c])
+        for k in range(4):
+            if k != c:
+                G = -D[:, k, c] / (lam[:, c] - lam[:, k])
+                grad = grad + G[:, None, None] * _polar_rotation(VB2[:, :, k], VB2[:, :, c])
+    return ce, grad
+
+
 def fisher_nll_grad_closed_form(A, R, overreg):
     """d nll / dA = -R + overreg * U diag(g1,g2,g3) V^T with the proper (U,s,V)
     (SURVEY.md A.4); per-sample gradient, no batch mean."""

@@ -25,6 +25,7 @@ SIGNATURES = {
     "suhpe_proper_svd_f32": (ctypes.c_int, [c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_fisher_fused_f32": (ctypes.c_int, [c_vp, c_vp, i64, f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_fisher_from_s_f32": (ctypes.c_int, [c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "suhpe_fisher_ce_f32": (ctypes.c_int, [c_vp, c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_laplace_nll_f32": (ctypes.c_int, [c_vp, c_vp, i64, c_vp, i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_select_init": (ctypes.c_int, [c_vp, u64, c_vp]),
     "suhpe_select_hist_f32": (ctypes.c_int, [c_vp, i64, i32, c_vp, c_vp, c_vp]),
@@ -46,6 +47,8 @@ SIGNATURES = {
 EINVAL = -100000
 STATUS_NONFINITE = 1
 STATUS_TRACE_RANGE = 2
+STATUS_NONFINITE_CE = 4
+FISHER_CE_WORKSPACE_FLOATS = 10
 HIST_BINS = 2048
 SELECT_STATE_BYTES = 32
 

@@ -36,6 +36,8 @@ def _raise_from_status(status, what):
                 f"{what}: the input contains non-finite values (torch.svd in the reference fails the same way)")
         if bits & _capi.STATUS_TRACE_RANGE:
             raise ValueError("A matrix has trace outside valid range [-1-eps,3+eps].")
+        if bits & _capi.STATUS_NONFINITE_CE:
+            raise AssertionError(f"{what}: the cross entropy is NaN or Inf (the reference asserts: fisher_utils.py:98)")
 
 
 def fisher_fused(A, R=None, overreg=1.0, *, nll=False, grad=False, rot=False, entropy=False,
@@ -67,6 +69,26 @@ def fisher_fused(A, R=None, overreg=1.0, *, nll=False, grad=False, rot=False, en
             ptr(out.get("rot")), ptr(out.get("entropy")), ptr(out.get("logC")), ptr(out.get("S")),
             ptr(out.get("G")), ptr(hist), ptr(status), stream()), what)
     _raise_from_status(status, what)
+    return out
+
+
+def fisher_ce(A1, A2, *, grad=False):
+    """fisher_CE value (n,) and, on request, d ce_i / d A2_i (n,9): two K2 launches + the closing kernel."""
+    T9, P9 = as_records(A1, "A1"), as_records(A2, "A2")
+    n = P9.shape[0]
+    if T9.shape[0] != n:
+        raise RuntimeError(f"shape mismatch: A1 has {T9.shape[0]} matrices, A2 has {n}")
+    dev = P9.device
+    out = {"ce": torch.empty(n, dtype=torch.float32, device=dev)}
+    if grad: out["grad"] = torch.empty((n, 9), dtype=torch.float32, device=dev)
+    if n == 0:
+        return out
+    work = torch.empty(_capi.FISHER_CE_WORKSPACE_FLOATS * n, dtype=torch.float32, device=dev)
+    status = _status_word(dev)
+    with torch.cuda.device(dev):
+        check(lib().suhpe_fisher_ce_f32(ptr(T9), ptr(P9), n, ptr(out["ce"]), ptr(out.get("grad")), ptr(work),
+                                        ptr(status), stream()), "fisher_CE")
+    _raise_from_status(status, "fisher_CE")
     return out
 
 

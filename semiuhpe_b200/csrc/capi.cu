@@ -14,7 +14,8 @@ namespace {
 
 static_assert(sizeof(SelectState) == SUHPE_SELECT_STATE_BYTES, "SelectState layout is part of the ABI");
 static_assert(kHistBinsMax == SUHPE_HIST_BINS, "histogram width is part of the ABI");
-static_assert(kStatusNonFinite == SUHPE_STATUS_NONFINITE && kStatusTraceRange == SUHPE_STATUS_TRACE_RANGE, "status bits");
+static_assert(kStatusNonFinite == SUHPE_STATUS_NONFINITE && kStatusTraceRange == SUHPE_STATUS_TRACE_RANGE &&
+              kStatusNonFiniteCE == SUHPE_STATUS_NONFINITE_CE, "status bits");
 
 // negligible-node cut of the Fisher quadrature (see cut_threshold in so3_math.cuh); process-wide
 static int g_cut_bits = 26;
@@ -225,6 +226,26 @@ int suhpe_fisher_from_s_f32(const float* S, int64_t n, float* logC, float* G, fl
     p.logC = logC; p.G = G; p.entropy = entropy; p.status = status;
     p.cut_bits = g_cut_bits;
     return rc(launch_fisher_fused(p, st(stream)));
+}
+
+int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
+                        float* workspace, int* status, void* stream) {
+    if (n < 0 || (n > 0 && (!A1 || !A2 || !ce || !workspace))) return SUHPE_EINVAL;
+    if (n == 0) return 0;
+    float* G1 = workspace;                     // (n,3)
+    float* S2 = workspace + 3 * n;             // (n,3)
+    float* G2 = workspace + 6 * n;             // (n,3)
+    float* H2 = workspace + 9 * n;             // (n)
+    FisherArgs t{};
+    t.A = A1; t.n = (long long)n; t.overreg = 1.0f; t.G = G1; t.status = status; t.cut_bits = g_cut_bits;
+    cudaError_t e = launch_fisher_fused(t, st(stream));
+    if (e != cudaSuccess) return rc(e);
+    FisherArgs q{};
+    q.A = A2; q.n = (long long)n; q.overreg = 1.0f; q.S = S2; q.G = G2; q.entropy = H2; q.status = status; q.cut_bits = g_cut_bits;
+    e = launch_fisher_fused(q, st(stream));
+    if (e != cudaSuccess) return rc(e);
+    FisherCeArgs c{A1, A2, (long long)n, G1, S2, G2, H2, ce, gradA2, status};
+    return rc(launch_fisher_ce_close(c, st(stream)));
 }
 
 int suhpe_laplace_nll_f32(const float* A, const float* Rgt, int64_t n, const float* grid, int32_t N,

@@ -467,6 +467,63 @@ proper_svd_kernel(SvdArgs p) {
 }
 
 // ---------------------------------------------------------------------------
+// fisher_CE closing kernel: thread per pair.  The two quadratures (target and
+// prediction) are K2 launches; this step re-derives both proper SVDs (registers, same routine),
+// builds the two quaternion frames and evaluates fisher_ce_close (so3_math.cuh).  HBM-bound:
+// 72 B of parameters + 40 B of statistics in, 4 + 36 B out per pair.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSvdThreads)
+fisher_ce_close_kernel(FisherCeArgs p, bool vec_ok) {
+    __shared__ SvdScratch scratch[kSvdWarps];        // a: A1 in -> gradient out, r: A2 in
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    SvdScratch& ws = scratch[warp];
+    const long long warps_total = (long long)gridDim.x * kSvdWarps;
+    const long long tiles = (p.n + 31) / 32;
+    int flags = 0;
+    for (long long tile = (long long)blockIdx.x * kSvdWarps + warp; tile < tiles; tile += warps_total) {
+        const long long base = tile * 32;
+        const int count = (int)min(32LL, p.n - base);
+        load_tile(ws.a, p.A1 + base * 9, count, vec_ok, lane);
+        load_tile(ws.r, p.A2 + base * 9, count, vec_ok, lane);
+        __syncwarp();
+        float grad[9];
+        if (lane < count) {
+            const long long i = base + lane;
+            float A[9], U1[9], V1[9], U2[9], V2[9], s1[3], s2[3];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) A[k] = ws.a[lane * 9 + k];
+            if (!proper_svd3(A, U1, V1, s1)) flags |= kStatusNonFinite;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) A[k] = ws.r[lane * 9 + k];
+            if (!proper_svd3(A, U2, V2, s2)) flags |= kStatusNonFinite;
+            const float g1[3] = {__ldg(p.G1 + 3 * i), __ldg(p.G1 + 3 * i + 1), __ldg(p.G1 + 3 * i + 2)};
+            const float g2[3] = {__ldg(p.G2 + 3 * i), __ldg(p.G2 + 3 * i + 1), __ldg(p.G2 + 3 * i + 2)};
+            // the singular values the statistics were computed for (same routine, same input; read
+            // back rather than assumed bit-identical across the two compilations)
+            s2[0] = __ldg(p.S2 + 3 * i); s2[1] = __ldg(p.S2 + 3 * i + 1); s2[2] = __ldg(p.S2 + 3 * i + 2);
+            // log f(s2) from K2's entropy H = log f + sum_j s_j (1 - g_j): the correction is O(1), so
+            // nothing cancels (logC - sum(s) would lose the leading digits for concentrated densities)
+            const float logf2 = __ldg(p.H2 + i) - fmaf(s2[0], 1.0f - g2[0], fmaf(s2[1], 1.0f - g2[1], s2[2] * (1.0f - g2[2])));
+            const float ce = fisher_ce_close(U1, V1, g1, U2, V2, s2, g2, logf2, p.grad ? grad : nullptr);
+            if (!(fabsf(ce) <= 3.402823466e38f)) flags |= kStatusNonFiniteCE;
+            p.ce[i] = ce;
+        }
+        __syncwarp();
+        if (p.grad) {
+            if (lane < count) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) ws.a[lane * 9 + k] = grad[k];
+            }
+            __syncwarp();
+            store_tile(p.grad + base * 9, ws.a, count, vec_ok, lane);
+        }
+        __syncwarp();
+    }
+    if (flags && p.status) atomicOr(p.status, flags);
+}
+
+// ---------------------------------------------------------------------------
 // Body probe (bench/profiling aid): the W2 pass body of one run type in a tight loop, tables in
 // shared memory, no per-sample glue.  variant bits: 0-1 type, 2 skip LDS, 3 skip MUFU, 4 skip mask
 // ---------------------------------------------------------------------------
@@ -610,6 +667,19 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     // first radix-select pass over the entropies just written (they are still L2-resident)
     if (err == cudaSuccess && p.hist) err = launch_select_hist_accumulate(p.entropy, p.n, p.hist, stream);
     return err;
+}
+
+cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    const int sms = sm_count();
+    const long long tiles = (p.n + 31) / 32;
+    long long blocks = (tiles + kSvdWarps - 1) / kSvdWarps;
+    const long long max_blocks = (long long)sms * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec_ok = aligned(p.A1) && aligned(p.A2) && aligned(p.grad);
+    fisher_ce_close_kernel<<<(unsigned)blocks, kSvdThreads, 0, stream>>>(p, vec_ok);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream) {

@@ -8,6 +8,7 @@ namespace suhpe {
 // status bits written (atomicOr) by the kernels into an optional device word
 constexpr int kStatusNonFinite  = 1;   // A held NaN/Inf (reference: torch.svd raises)
 constexpr int kStatusTraceRange = 2;   // trace(R1 R2^T) outside [-1-1e-4, 3+1e-4] (pytorch3d raises ValueError)
+constexpr int kStatusNonFiniteCE = 4;  // a cross entropy came out NaN/Inf (reference: assert, fisher_utils.py:98)
 
 // radix-select digit layout over the 32-bit monotone entropy key: 11 | 11 | 10 bits
 constexpr int kHistBins1 = 2048, kHistShift1 = 21;
@@ -70,7 +71,22 @@ struct MetricsArgs {
     int* status;
 };
 
+// closing step of fisher_CE: per-pair frames, cross entropy and its gradient from the K2 statistics
+struct FisherCeArgs {
+    const float* A1;       // (n,9) target parameters (constants)
+    const float* A2;       // (n,9) predicted parameters
+    long long n;
+    const float* G1;       // (n,3) grad logC of A1          (K2)
+    const float* S2;       // (n,3) proper singular values of A2, G2 (n,3) grad logC, H2 (n) entropy   (K2)
+    const float* G2;
+    const float* H2;
+    float* ce;             // (n)
+    float* grad;           // (n,9) d ce_i / d A2_i | nullptr
+    int* status;
+};
+
 cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream);
+cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream);
 cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream);
 cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream);
 cudaError_t launch_metrics(MetricsArgs p, cudaStream_t stream);

@@ -542,6 +542,126 @@ SUHPE_HD FisherStats fisher_finish(const float* s, float F, float N0, float N1, 
 }
 
 // ----------------------------------------------------------------------------
+// Matrix-Fisher cross entropy through the Bingham form (src/fisher/fisher_utils.py:84-99,
+// src/fisher/bingham_utils.py:5-32, src/fisher/between_bingham_fisher.py:107-152), target A1,
+// prediction A2, value and gradient w.r.t. A2 in closed form.
+//
+// With the proper SVDs, g = grad logC (K2), the quaternion frames
+//   VB = [q(U V^T), q(U E_1 V^T), q(U E_2 V^T), q(U E_3 V^T)],  q(U E_k V^T) = (0,u_k) (x) q(U V^T)
+// (the Bingham-convention column order for s1 >= s2 >= |s3|), W = VB1^T VB2, the expected squared
+// projections of the target  gamma = 1/4 (1+g1+g2+g3, 1+g1-g2-g3, 1-g1+g2-g3, 1-g1-g2+g3)  and
+// LamB2 = -2 (s2+s3, s1+s3, s1+s2) of the prediction, the reference evaluates
+//   CE = log f(s_2) - sum_{i=1..3} LamB2_i [ gamma_0 W_0i^2 + sum_{j=1..3} gamma_j W_ij^2 ]
+// (W_ij, not W_ji: bingham_utils.py:27 takes a ROW of V1^T V2 where the expectation needs a
+// column; reproduced as is).  x^T K(A) x = <A, R(x)> is linear in A and (lam_c, v_c) are the
+// eigenpairs of K(A2), so by first-order perturbation
+//   dCE/dA2 = sum_c L_lam_c R~(v_c,v_c) + sum_{k != c} (v_k . L_v_c)/(lam_c - lam_k) R~(v_k,v_c)
+// with R~ the symmetric bilinear form of the quaternion -> rotation map.  This is what autograd
+// yields through torch.svd, matrix_to_quaternion and the quadrature's backward (oracle:
+// fisher_ce vs fisher_ce_closed_form agree to 6e-15 in fp64); quaternion signs cancel everywhere.
+// ----------------------------------------------------------------------------
+// unit quaternion (w,x,y,z) of a rotation matrix, largest-component branch
+SUHPE_HD void quat_of_rotation(const float* R, float* q) {
+    const float t0 = 1.0f + R[0] + R[4] + R[8], t1 = 1.0f + R[0] - R[4] - R[8];
+    const float t2 = 1.0f - R[0] + R[4] - R[8], t3 = 1.0f - R[0] - R[4] + R[8];
+    const float tm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+    if (tm == t0)      { q[0] = t0; q[1] = R[7] - R[5]; q[2] = R[2] - R[6]; q[3] = R[3] - R[1]; }
+    else if (tm == t1) { q[0] = R[7] - R[5]; q[1] = t1; q[2] = R[3] + R[1]; q[3] = R[2] + R[6]; }
+    else if (tm == t2) { q[0] = R[2] - R[6]; q[1] = R[3] + R[1]; q[2] = t2; q[3] = R[5] + R[7]; }
+    else               { q[0] = R[3] - R[1]; q[1] = R[6] + R[2]; q[2] = R[7] + R[5]; q[3] = t3; }
+    const float inv = div_rn(1.0f, sqrt_rn(fmaf(q[0], q[0], fmaf(q[1], q[1], fmaf(q[2], q[2], q[3] * q[3])))));
+    q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+
+// frame[c][0..3]: quaternion c of the Bingham frame of (U, V)
+SUHPE_HD void bingham_frame(const float* U, const float* V, float (*frame)[4]) {
+    float R0[9];
+    u_diag_vt(U, V, 1.f, 1.f, 1.f, R0);
+    quat_of_rotation(R0, frame[0]);
+    const float w = frame[0][0], x = frame[0][1], y = frame[0][2], z = frame[0][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float a0 = U[k], a1 = U[3 + k], a2 = U[6 + k];          // column k of U
+        frame[k + 1][0] = -(a0 * x + a1 * y + a2 * z);                 // (0,a) (x) (w,v) = (-a.v, w a + a x v)
+        frame[k + 1][1] = fmaf(w, a0, a1 * z - a2 * y);
+        frame[k + 1][2] = fmaf(w, a1, a2 * x - a0 * z);
+        frame[k + 1][3] = fmaf(w, a2, a0 * y - a1 * x);
+    }
+}
+
+// acc += coef * R~(p, q)
+SUHPE_HD void polar_rotation_axpy(float coef, const float* p, const float* q, float* acc) {
+    const float ww = p[0] * q[0], xx = p[1] * q[1], yy = p[2] * q[2], zz = p[3] * q[3];
+    const float xy = fmaf(p[1], q[2], p[2] * q[1]), xz = fmaf(p[1], q[3], p[3] * q[1]), yz = fmaf(p[2], q[3], p[3] * q[2]);
+    const float wx = fmaf(p[0], q[1], p[1] * q[0]), wy = fmaf(p[0], q[2], p[2] * q[0]), wz = fmaf(p[0], q[3], p[3] * q[0]);
+    acc[0] = fmaf(coef, (ww + xx) - (yy + zz), acc[0]);
+    acc[1] = fmaf(coef, xy - wz, acc[1]);
+    acc[2] = fmaf(coef, xz + wy, acc[2]);
+    acc[3] = fmaf(coef, xy + wz, acc[3]);
+    acc[4] = fmaf(coef, (ww + yy) - (xx + zz), acc[4]);
+    acc[5] = fmaf(coef, yz - wx, acc[5]);
+    acc[6] = fmaf(coef, xz - wy, acc[6]);
+    acc[7] = fmaf(coef, yz + wx, acc[7]);
+    acc[8] = fmaf(coef, (ww + zz) - (xx + yy), acc[8]);
+}
+
+// g1: grad logC of the target; s2, g2, logf2 = log f(s2): of the prediction.  grad may be null.
+SUHPE_HD float fisher_ce_close(const float* U1, const float* V1, const float* g1,
+                               const float* U2, const float* V2, const float* s2, const float* g2, float logf2,
+                               float* grad) {
+    float f1[4][4], f2[4][4], W[4][4];
+    bingham_frame(U1, V1, f1);
+    bingham_frame(U2, V2, f2);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            W[r][c] = fmaf(f1[r][0], f2[c][0], fmaf(f1[r][1], f2[c][1], fmaf(f1[r][2], f2[c][2], f1[r][3] * f2[c][3])));
+    const float gam[4] = {0.25f * (1.0f + g1[0] + g1[1] + g1[2]), 0.25f * (1.0f + g1[0] - g1[1] - g1[2]),
+                          0.25f * (1.0f - g1[0] + g1[1] - g1[2]), 0.25f * (1.0f - g1[0] - g1[1] + g1[2])};
+    const float lamB[4] = {0.0f, -2.0f * (s2[1] + s2[2]), -2.0f * (s2[0] + s2[2]), -2.0f * (s2[0] + s2[1])};
+    float phi[4] = {0.f, 0.f, 0.f, 0.f};
+    float second = 0.0f;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        phi[i] = fmaf(gam[0], W[0][i] * W[0][i],
+                      fmaf(gam[1], W[i][1] * W[i][1], fmaf(gam[2], W[i][2] * W[i][2], gam[3] * W[i][3] * W[i][3])));
+        second = fmaf(lamB[i], phi[i], second);
+    }
+    const float ce = logf2 - second;
+    if (grad) {
+        // eigenvalues of K(A2) in frame order; d s_m / d lam_c = 1/4 [[1,1,-1,-1],[1,-1,1,-1],[1,-1,-1,1]]
+        const float lam[4] = {s2[0] + s2[1] + s2[2], s2[0] - s2[1] - s2[2], -s2[0] + s2[1] - s2[2], -s2[0] - s2[1] + s2[2]};
+        const float h0 = 0.25f * (g2[0] - 1.0f), h1 = 0.25f * (g2[1] - 1.0f), h2 = 0.25f * (g2[2] - 1.0f);
+        const float Ll[4] = {(h0 + h1 + h2) + (phi[1] + phi[2] + phi[3]), (h0 - h1 - h2) - phi[1],
+                             (-h0 + h1 - h2) - phi[2], (-h0 - h1 + h2) - phi[3]};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) grad[k] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) polar_rotation_axpy(Ll[c], f2[c], f2[c], grad);
+        // off-diagonal terms: G_kc = -D_kc / (lam_c - lam_k), D_kc = v2_k . d(second)/d v2_c (zero for c = 0);
+        // R~ is symmetric in (k,c), so each unordered pair gets G_kc + G_ck
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = k + 1; c < 4; ++c) {
+                float Dkc = 2.0f * gam[0] * lamB[c] * W[0][c] * W[0][k];
+                float Dck = (k == 0) ? 0.0f : 2.0f * gam[0] * lamB[k] * W[0][k] * W[0][c];
+                float a = 0.0f;
+#pragma unroll
+                for (int i = 1; i < 4; ++i) a = fmaf(lamB[i], W[i][c] * W[i][k], a);
+                Dkc = fmaf(2.0f * gam[c], a, Dkc);
+                if (k != 0) Dck = fmaf(2.0f * gam[k], a, Dck);
+                const float den = lam[c] - lam[k];
+                // exact degeneracy (s_i = +-s_j): the reference's svd backward is 0/0 there; contribute nothing
+                const float G = (den != 0.0f) ? div_rn(Dck - Dkc, den) : 0.0f;   // -Dkc/den - Dck/(-den)
+                polar_rotation_axpy(G, f2[k], f2[c], grad);
+            }
+    }
+    return ce;
+}
+
+// ----------------------------------------------------------------------------
 // Rotation-Laplace grid sum (src/laplace/rotation_laplace.py:58-72,140-173 and its autograd
 // backward).  Per (sample, grid point k):
 //   d_k = T - <A,R_k>,  q_k = sqrt(max(d_k, 1e-8)),  w_k = exp(-q_k)/q_k

@@ -1,8 +1,8 @@
 """Drop-in for the reference's ``src/fisher/fisher_utils.py`` on CUDA tensors.
 
 Same names, arguments and return shapes; every function is ONE kernel launch
-(K1 or K2 of ``csrc/fisher_kernels.cu``) instead of the reference's CPU SVD
-round trips and hundreds of elementwise ops.  Differences that are deliberate:
+(K1 or K2 of ``csrc/fisher_kernels.cu``; ``fisher_CE`` is three) instead of the
+reference's CPU SVD round trips and hundreds of elementwise ops.  Differences that are deliberate:
 
 * inputs must be CUDA fp32 (the reference moves them to the CPU itself);
 * ``fisher_entropy`` / ``batch_torch_A_to_R`` return plain tensors without a
@@ -78,10 +78,32 @@ def fisher_nll_entropy(net_out, R, overreg=1.05):
     return out["nll"], out["rot"], out["entropy"]
 
 
+class _FisherCE(torch.autograd.Function):
+    """ce_i and d ce_i / d A2_i from the same three launches."""
+
+    @staticmethod
+    def forward(ctx, A1, A2):
+        need_grad = ctx.needs_input_grad[1]
+        out = _ops.fisher_ce(A1, A2, grad=need_grad)
+        if need_grad:
+            ctx.save_for_backward(out["grad"])
+        ctx.a_shape = A2.shape
+        return out["ce"]
+
+    @staticmethod
+    def backward(ctx, g_ce):
+        (grad,) = ctx.saved_tensors
+        return None, (grad * g_ce.reshape(-1, 1)).view(ctx.a_shape)
+
+
 def fisher_CE(A1, A2):
-    """Cross entropy between two matrix-Fisher distributions (reference
-    fisher_utils.py:84-99).  SURVEY.md section 8(f) ranks it 'next' (needs the quaternion
-    frames and a backward through U,V); not on the path built so far."""
-    raise NotImplementedError(
-        "fisher_CE is outside the hot path implemented in this round (SURVEY.md 8f-1); "
-        "use type_unsuper='nll' or the reference's fisher_CE")
+    """Cross entropy h(f1, f2) of two matrix-Fisher densities, A1 the target and A2 the
+    prediction, (b,9)|(b,3,3) x2 -> (b,)  -- reference fisher_utils.py:84-99 (the default
+    unsupervised loss, src/agent.py:155).  Differentiable w.r.t. A2 like the reference (through the
+    SVD, the quaternion frame and logC_F, here in closed form).  A1 is a constant: the agent feeds
+    the detached teacher prediction (src/agent.py:107); asking for its gradient is an error rather
+    than a silent zero.  NaN/Inf results raise AssertionError as in the reference (:98)."""
+    if isinstance(A1, torch.Tensor) and A1.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("fisher_CE: the gradient w.r.t. the target A1 is not implemented "
+                                  "(the reference's training loop detaches it, src/agent.py:107)")
+    return _FisherCE.apply(A1, A2)

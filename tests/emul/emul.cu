@@ -193,6 +193,20 @@ void emul_fisher(const float* A, const float* Rgt, long n, float overreg, int cu
     }
 }
 
+// fisher_CE(A1 target, A2 prediction): value and gradient w.r.t. A2, with the kernels' per-sample math
+void emul_fisher_ce(const float* A1, const float* A2, long n, int cut_bits, float* ce, float* grad) {
+    for (long i = 0; i < n; ++i) {
+        float u1[9], v1[9], s1[3], u2[9], v2[9], s2[3], F, N0, N1, N2;
+        proper_svd3(A1 + 9 * i, u1, v1, s1);
+        quadrature(s1, cut_bits, &F, &N0, &N1, &N2);
+        const FisherStats t = fisher_finish(s1, F, N0, N1, N2);
+        proper_svd3(A2 + 9 * i, u2, v2, s2);
+        quadrature(s2, cut_bits, &F, &N0, &N1, &N2);
+        const FisherStats p = fisher_finish(s2, F, N0, N1, N2);
+        ce[i] = fisher_ce_close(u1, v1, t.g, u2, v2, s2, p.g, p.logf, grad + 9 * i);
+    }
+}
+
 void emul_quad_nodes(float* x) { for (int i = 0; i < 512; ++i) x[i] = quad_node((float)i); }
 
 void emul_i0e(const float* a, long n, float* out) {

@@ -19,6 +19,10 @@ laplace.npz  NLL_loss("RLaplace") fwd+bwd, analytical_mode, log_pdf("RFisher")
              on the reference's own 4608-point grid (src/laplace/rotation_laplace.py,
              src/laplace/eq_grids2.npy; the grid is stored as a fixture INPUT)
 select.npz   pool threshold by the literal lines src/agent.py:405-407, masks by :148
+fisher_ce.npz  fisher_CE(A1 target, A2 prediction) and its autograd gradient w.r.t. A2
+             (src/fisher/fisher_utils.py:84-99; quaternion frames through the restated
+             pytorch3d matrix_to_quaternion -- the value and the gradient do not depend on its
+             branch or sign choices), plus fp64 anchors from the oracle's restatement
 metrics.npz  compute_euler_angles_from_rotation_matrices (src/utils.py:232),
              compute_err_deg_from_matrices (src/agent.py:447-455, extracted by AST),
              so3_relative_angle via the restated pytorch3d (PARITY UNPINNED for that
@@ -97,6 +101,42 @@ def make_fisher(ref):
         Rest=Rest.detach().numpy(), entropy=ent.detach().numpy(), logpdf=logpdf.detach().numpy(),
         S=s.numpy(), logC=logc.detach().numpy(), dlogC=sl.grad.numpy())
     print("fisher.npz", A.shape[0], "samples")
+
+
+def make_fisher_ce(ref):
+    """Teacher / student parameter pairs: student near the teacher (the training regime),
+    unrelated frames, and students with close singular values (gradient tolerance class 1e-4)."""
+    from oracle import so3_oracle as orc
+    fu = ref.fisher_utils
+    gen = torch.Generator().manual_seed(20240612)
+    t, p, names = [], [], []
+    for scale in (1.0, 10.0, 30.0):
+        a1 = scale * torch.randn(96, 3, 3, generator=gen)
+        t.append(a1); p.append(a1 + 0.25 * scale * torch.randn(96, 3, 3, generator=gen))
+        names += [f"near{int(scale)}"] * 96
+    kappa = 5 + 45 * torch.rand(96, 1, 1, generator=gen)
+    R0 = random_rotations(96, gen)
+    t.append(kappa * R0 + 0.5 * torch.randn(96, 3, 3, generator=gen))
+    p.append((kappa * (0.6 + 0.8 * torch.rand(96, 1, 1, generator=gen))) * R0 + 1.5 * torch.randn(96, 3, 3, generator=gen))
+    names += ["realistic"] * 96
+    t.append(10 * torch.randn(96, 3, 3, generator=gen)); p.append(10 * torch.randn(96, 3, 3, generator=gen))
+    names += ["unrelated"] * 96
+    Ud, Vd = random_rotations(48, gen), random_rotations(48, gen)
+    sv = torch.tensor([[10.0, 10.0 - 1e-2, 3.0], [10.0, 5.0, 5.0 - 1e-2], [8.0, 8.0 - 1e-2, 8.0 - 2e-2],
+                       [20.0, 3.0, 1e-2], [20.0, 3.0, -1e-2], [12.0, 6.0, -5.99]]).repeat(8, 1)
+    p.append(Ud @ torch.diag_embed(sv) @ Vd.transpose(1, 2)); t.append(8 * torch.randn(48, 3, 3, generator=gen))
+    names += ["student_neardegenerate"] * 48
+    A1, A2 = torch.cat(t).contiguous(), torch.cat(p).contiguous()
+    leaf = A2.clone().requires_grad_(True)
+    ce = fu.fisher_CE(A1.clone(), leaf)
+    ce.sum().backward()
+    leaf64 = A2.double().requires_grad_(True)
+    ce64 = orc.fisher_ce(A1.double(), leaf64)
+    ce64.sum().backward()
+    np.savez_compressed(os.path.join(HERE, "fisher_ce.npz"), A1=A1.numpy(), A2=A2.numpy(), names=np.array(names),
+                        ce=ce.detach().numpy(), grad=leaf.grad.numpy(),
+                        ce64=ce64.detach().numpy(), grad64=leaf64.grad.numpy())
+    print("fisher_ce.npz", A1.shape[0], "pairs")
 
 
 def make_laplace(ref):
@@ -216,7 +256,6 @@ def make_metrics(ref):
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixed reduction order inside the reference's torch ops
     ref = ref_shim.load()
-    make_fisher(ref)
-    make_laplace(ref)
-    make_select(ref)
-    make_metrics(ref)
+    makers = dict(fisher=make_fisher, fisher_ce=make_fisher_ce, laplace=make_laplace, select=make_select, metrics=make_metrics)
+    for name in (sys.argv[1:] or list(makers)):          # `make_golden.py fisher_ce` regenerates one file
+        makers[name](ref)

@@ -60,11 +60,12 @@ def test_no_cpu_fallback(built):
     A, R = torch.randn(4, 9), torch.eye(3).repeat(4, 1, 1)
     for call in (lambda: vmf_loss(A, R), lambda: fisher_entropy(A), lambda: batch_torch_A_to_R(A),
                  lambda: NLL_loss("RLaplace", A, R, R), lambda: compute_err_deg_from_matrices(R, R),
+                 lambda: fisher_CE(A, A),
                  lambda: entropy_threshold(torch.randn(10), 0.5), lambda: entropy_mask(torch.randn(10), 0.0)):
         with pytest.raises(RuntimeError, match="CUDA"):
             call()
-    with pytest.raises(NotImplementedError):
-        fisher_CE(A, A)
+    with pytest.raises(NotImplementedError):              # the target is a constant (src/agent.py:107)
+        fisher_CE(A.clone().requires_grad_(True), A)
 
 
 def test_product_never_imports_oracle():

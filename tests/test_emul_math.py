@@ -245,3 +245,23 @@ def test_degrees_conversion_is_the_reference_rounding(emul):
     emul.emul_rad_to_deg(P(rad), ctypes.c_long(len(rad)), P(out))
     ref = (torch.from_numpy(rad) * 180 / np.pi).numpy()
     np.testing.assert_array_equal(out, ref)
+
+
+def test_fisher_ce_against_golden(emul, golden):
+    """The kernels' closed-form fisher_CE (SVD, quadrature, frames, eigenpair perturbation) on the host
+    against the reference's value and autograd gradient."""
+    g = golden("fisher_ce")
+    n = len(g["A1"])
+    a1 = np.ascontiguousarray(g["A1"].reshape(n, 9))
+    a2 = np.ascontiguousarray(g["A2"].reshape(n, 9))
+    ce, grad = np.zeros(n, np.float32), np.zeros((n, 9), np.float32)
+    emul.emul_fisher_ce(P(a1), P(a2), ctypes.c_long(n), ctypes.c_int(26), P(ce), P(grad))
+    # value: 1e-5, or no further from fp64 than the reference's own fp32 result (large |CE| rows)
+    ok, _ = np.abs(ce - g["ce"]) <= ATOL + RTOL * np.abs(g["ce"]), None
+    assert (ok | no_worse_than_reference(ce, g["ce"], g["ce64"])).all()
+    err64 = grad_rel_err(grad, g["grad64"])
+    ref_err64 = grad_rel_err(g["grad"], g["grad64"])
+    stable = g["names"] != "student_neardegenerate"
+    assert (err64[stable] <= np.maximum(2 * ref_err64[stable], 2e-5)).all()
+    # near-degenerate students: 1/(s_i - s_j) amplifies fp32 rounding sample by sample; compare the class
+    assert err64[~stable].max() <= max(2 * ref_err64[~stable].max(), 1e-4)

@@ -56,6 +56,28 @@ def test_entropy_closed_form_matches_chain(golden):
     np.testing.assert_allclose(g["grad"][keep], grad64.numpy(), rtol=1e-4, atol=2e-6)
 
 
+def test_fisher_ce_golden(golden):
+    """fisher_CE: the op-by-op restatement reproduces the reference's value and its
+    autograd gradient w.r.t. the prediction; the closed form the kernel evaluates equals the
+    restatement's fp64 autograd to rounding."""
+    g = golden("fisher_ce")
+    A1, A2 = torch.from_numpy(g["A1"]), torch.from_numpy(g["A2"])
+    leaf = A2.clone().requires_grad_(True)
+    ce = orc.fisher_ce(A1, leaf)
+    ce.sum().backward()
+    np.testing.assert_allclose(ce.detach().numpy(), g["ce"], rtol=5e-6, atol=5e-6)
+    stable = g["names"] != "student_neardegenerate"
+    scale = np.abs(g["grad"]).reshape(len(A1), -1).max(1)[:, None, None]
+    assert (np.abs(leaf.grad.numpy() - g["grad"]) / scale)[stable].max() < 2e-5
+    ce64, grad64 = orc.fisher_ce_closed_form(A1.double(), A2.double())
+    np.testing.assert_allclose(ce64.numpy(), g["ce64"], rtol=1e-11, atol=1e-11)
+    scale64 = np.abs(g["grad64"]).reshape(len(A1), -1).max(1)[:, None, None]
+    assert (np.abs(grad64.numpy() - g["grad64"]) / scale64).max() < 1e-9
+    # h(f, f) is the entropy of f: the row/column quirk of bingham_utils.py:27 is invisible when both frames coincide
+    same = orc.fisher_ce(A1[:64], A1[:64].clone())
+    np.testing.assert_allclose(same.numpy(), orc.fisher_entropy(A1[:64]).numpy(), rtol=1e-5, atol=2e-5)
+
+
 def test_laplace_golden(golden):
     g = golden("laplace")
     A, R, grids = (torch.from_numpy(g[k]) for k in ("A", "R", "grids"))
