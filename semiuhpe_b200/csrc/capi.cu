@@ -356,7 +356,7 @@ int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk) {
     if (!p) return SUHPE_EINVAL;
     memset(p, 0, sizeof(*p));
     if (chunk > max_n) chunk = max_n;
-    chunk = (chunk + 31) & ~31LL;                 // keep every chunk base 16-byte aligned (32 records = 1152 B)
+    chunk = (chunk + 127) & ~127LL;               // chunk bases (and quarter chunks) stay 16-byte aligned: 32 records = 1152 B
     p->max_n = max_n; p->chunk = chunk;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(q, bytes); };
@@ -397,15 +397,28 @@ int suhpe_fisher_pool_host(suhpe_pipeline* p, const float* A_host, const float* 
         CK(cudaEventRecord(p->ev_user, user));
         CK(cudaStreamWaitEvent(p->s_k, p->ev_user, 0));
     }
-    const long long nchunks = (n + p->chunk - 1) / p->chunk;
+    // Chunk schedule: the pipeline's fill (first H2D copy) and drain (last D2H copy) are exposed
+    // latency, so the pool starts and ends with quarter and half chunks and runs full chunks between.
+    long long sched[8];
+    int ramp = 0;
+    const long long q = p->chunk / 4;                 // chunk is a multiple of 128: q keeps 16-byte alignment
+    if (n >= 4 * p->chunk && q > 0) { sched[0] = q; sched[1] = 2 * q; ramp = 2; }
+    const long long body = n - (ramp ? 6 * q : 0);    // head q + 2q, tail 2q + q
+    const long long nbody = (body + p->chunk - 1) / p->chunk;
+    const long long nchunks = nbody + 2 * ramp;
+    long long base = 0;
     for (long long c = 0; c < nchunks && e == cudaSuccess; ++c) {
         const int b = (int)(c % NB);
-        const long long base = c * p->chunk;
-        const long long cnt = (n - base < p->chunk) ? (n - base) : p->chunk;
+        long long cnt;
+        if (c < ramp) cnt = sched[c];
+        else if (c < ramp + nbody) { const long long done = (c - ramp) * p->chunk; cnt = (body - done < p->chunk) ? (body - done) : p->chunk; }
+        else cnt = (c == nchunks - 1) ? q : 2 * q;
+        const long long this_base = base;
+        base += cnt;
         // inputs: the buffer is free once the kernel of its previous chunk has run
         if (c >= NB) CK(cudaStreamWaitEvent(p->s_in, p->ev_k[b], 0));
-        CK(cudaMemcpyAsync(p->dA[b], A_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
-        if (Rgt_host) CK(cudaMemcpyAsync(p->dR[b], Rgt_host + base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
+        CK(cudaMemcpyAsync(p->dA[b], A_host + this_base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
+        if (Rgt_host) CK(cudaMemcpyAsync(p->dR[b], Rgt_host + this_base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
         CK(cudaEventRecord(p->ev_in[b], p->s_in));
         // kernel: after its inputs landed and the previous outputs of this buffer were drained
         CK(cudaStreamWaitEvent(p->s_k, p->ev_in[b], 0));
@@ -414,15 +427,15 @@ int suhpe_fisher_pool_host(suhpe_pipeline* p, const float* A_host, const float* 
         a.A = p->dA[b]; a.Rgt = Rgt_host ? p->dR[b] : nullptr; a.n = cnt; a.overreg = overreg;
         a.nll = nll_host ? p->dNll[b] : nullptr;
         a.grad = grad_host ? p->dGrad[b] : nullptr;
-        a.entropy = ent_dev + base;
+        a.entropy = ent_dev + this_base;
         a.hist = reinterpret_cast<unsigned long long*>(hist_dev); a.status = status_dev; a.cut_bits = g_cut_bits;
         CK(launch_fisher_fused(a, p->s_k));
         CK(cudaEventRecord(p->ev_k[b], p->s_k));
         // outputs
         CK(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0));
-        if (nll_host) CK(cudaMemcpyAsync(nll_host + base, p->dNll[b], (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
-        if (grad_host) CK(cudaMemcpyAsync(grad_host + base * 9, p->dGrad[b], (size_t)cnt * 36, cudaMemcpyDeviceToHost, p->s_out));
-        if (entropy_host) CK(cudaMemcpyAsync(entropy_host + base, ent_dev + base, (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
+        if (nll_host) CK(cudaMemcpyAsync(nll_host + this_base, p->dNll[b], (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
+        if (grad_host) CK(cudaMemcpyAsync(grad_host + this_base * 9, p->dGrad[b], (size_t)cnt * 36, cudaMemcpyDeviceToHost, p->s_out));
+        if (entropy_host) CK(cudaMemcpyAsync(entropy_host + this_base, ent_dev + this_base, (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
         CK(cudaEventRecord(p->ev_out[b], p->s_out));
     }
     if (external) CK(cudaStreamWaitEvent(user, p->ev_k[(nchunks - 1) % NB], 0));

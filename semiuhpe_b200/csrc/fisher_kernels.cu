@@ -274,15 +274,21 @@ fisher_fused_kernel(FisherArgs p) {
     unsigned tab2_s = (unsigned)__cvta_generic_to_shared(&tb) + 8u * lane;          // float2 column
     unsigned desc_s = (unsigned)__cvta_generic_to_shared(ws.desc);
     asm volatile("" : "+r"(tab_s), "+r"(tab2_s), "+r"(desc_s));
+    // Schedule: `full_rounds` rounds in which every warp of the grid takes one 32-sample tile, then ONE
+    // closing round that spreads the remaining samples evenly over all warps (samples_per_warp < 32
+    // each), so every warp finishes together whatever n is (a plain round-robin of 32-sample tiles
+    // costs a whole extra round for the leftover: 8 % at 2^20 samples).  Small batches are the
+    // special case full_rounds = 0.
     const long long warps_total = (long long)gridDim.x * kWarpsPerBlock;
     const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + warp;
     const int spw = p.samples_per_warp;
-    const long long tiles = (p.n + spw - 1) / spw;
     bool bad = false;
 
-    for (long long tile = gwarp; tile < tiles; tile += warps_total) {
-        const long long base = tile * spw;
-        const int count = (int)min((long long)spw, p.n - base);
+    for (long long round = 0; round <= p.full_rounds; ++round) {
+        const bool closing = round == p.full_rounds;
+        const long long base = closing ? p.full_rounds * warps_total * 32 + gwarp * spw : (round * warps_total + gwarp) * 32;
+        const int count = closing ? (int)max(0LL, min((long long)spw, p.n - base)) : 32;
+        if (count == 0) break;
         const bool mine = lane < count;
 
         // ---- phase 1: load + SVD + run descriptors (thread per sample) ---------
@@ -649,19 +655,18 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     static_assert(kSmem <= 227 * 1024, "fisher_fused_kernel shared memory exceeds one SM");
     cudaError_t err = cudaFuncSetAttribute(fisher_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (err != cudaSuccess) return err;
-    // one persistent CTA of 20 warps per SM (the node tables are shared by the whole CTA)
-    const long long resident_warps = (long long)sms * kWarpsPerBlock;
-    // small batches: spread samples over as many warps as possible (latency);
-    // large batches: 32 samples per warp so the tile I/O is float4-coalesced
-    long long spw = (p.n + resident_warps - 1) / resident_warps;
-    if (spw < 1) spw = 1;
-    if (spw > 32 || p.n >= resident_warps * 8) spw = 32;
-    p.samples_per_warp = (int)spw;
-    const long long tiles = (p.n + spw - 1) / spw;
-    long long blocks = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    // one persistent CTA of 20 warps per SM (the node tables are shared by the whole CTA); small
+    // batches get one sample per warp on as many SMs as that takes (latency)
+    long long blocks = (p.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > sms) blocks = sms;
+    const long long warps_total = blocks * kWarpsPerBlock;
+    // full rounds of 32-sample tiles (float4-coalesced tile I/O), then the leftover spread evenly
+    p.full_rounds = p.n / (warps_total * 32);
+    const long long rest = p.n - p.full_rounds * warps_total * 32;
+    const long long spw = (rest + warps_total - 1) / warps_total;    // 0..32
+    p.samples_per_warp = (int)spw;
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    p.vec_ok = (spw == 32) && aligned(p.A) && aligned(p.Rgt) && aligned(p.grad) && aligned(p.Rout);
+    p.vec_ok = aligned(p.A) && aligned(p.Rgt) && aligned(p.grad) && aligned(p.Rout);
     fisher_fused_kernel<<<(unsigned)blocks, kThreads, kSmem, stream>>>(p);
     err = cudaGetLastError();
     // first radix-select pass over the entropies just written (they are still L2-resident)

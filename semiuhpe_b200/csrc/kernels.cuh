@@ -32,7 +32,8 @@ struct FisherArgs {
     unsigned long long* hist;  // (2048) += histogram of the top 11 key bits of entropy | nullptr
     int* status;           // |= kStatus* | nullptr
     int cut_bits;          // negligible-node cut: skipped mass < 2^-cut_bits of the normaliser sum; <= 0 = off
-    int samples_per_warp;  // set by the launcher
+    long long full_rounds; // set by the launcher: rounds of one 32-sample tile per warp
+    int samples_per_warp;  // set by the launcher: samples per warp in the closing round (0..32)
     bool vec_ok;           // set by the launcher: float4 tile I/O allowed
 };
 

@@ -91,9 +91,9 @@ def test_fisher_ce_full_size_properties(cuda):
     ce.sum().backward()
     m = 4096
     d = torch.randn(m, 9, device=cuda, generator=gen)
-    h = 1e-2
+    h = 5e-2                                   # fp32 values: rounding noise ~5e-6 / 2h against O(h^2) truncation
     with torch.no_grad():
         fd = (fisher_CE(A1[:m], A2[:m] + h * d) - fisher_CE(A1[:m], A2[:m] - h * d)) / (2 * h)
     an = (A2.grad[:m] * d).sum(1)
     scale = A2.grad[:m].abs().max(1)[0] * d.abs().max(1)[0]
-    assert float(((fd - an).abs() / scale).median()) < 5e-3
+    assert float(((fd - an).abs() / scale).median()) < 1e-2
