@@ -78,6 +78,11 @@ int suhpe_set_quadrature_cut_bits(int bits);
 int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
                         float* workspace, int* status, void* stream);
 
+/* Rotate-augmentation adjustment of the teacher's parameter matrices before they become pseudo
+ * labels (src/agent.py:110-119): mode 0 (train_labeled "DAD3DHeads") out = aug_rot * pred;
+ * mode 1 ("300WLP") out = (D aug_rot D pred^T)^T with D = diag(1,-1,-1).  All (n,9) row-major. */
+int suhpe_rotate_adjust_f32(const float* pred, const float* aug_rot, int64_t n, int32_t mode, float* out, void* stream);
+
 /* K2 on given singular values: logC_F(S) and its backward G = dlogC/dS, entropy(S)
  * (src/fisher/torch_norm_factor.py:66-92 `logC_F`; S (n,3) sorted s1>=s2>=|s3| like every
  * reference call site).  Outputs nullable. */
@@ -117,10 +122,14 @@ int suhpe_entropy_mask_f32(const float* entropy, int64_t n, const float* thr_dev
 /* K4 -- error metrics over rotation pairs.
  *   geo_deg  rad2deg(so3_relative_angle(Rp,Rg))       src/agent.py:449-451, eval.py:88-89
  *   frob     ||I - Rp Rg^T||_F                        eval.py:93-98
- *   euler    (pitch,yaw,roll) radians of Rp           src/utils.py:232-260
+ *   euler    (pitch,yaw,roll) radians of Rp           src/utils.py:232-260   (full_range 0 | 1)
+ *            full_range = 2 (SUHPE_EULER_DAD): the DAD-trained convention of eval.py:66-74 --
+ *            scipy as_euler("xyz") of Rp^T, [roll,pitch,yaw] = limit_angle([a2, a0-180, a1]) -- in
+ *            DEGREES; abs_err / mae then compare against gt_euler directly
  *   abs_err  |euler*180/pi - gt_euler|, mae = mean_3  src/agent.py:452-454, eval.py:76-83
  *   sums[8] += {geo, frob, |dpitch|, |dyaw|, |droll|, mae, 0, 0} in fp64 (eval.py:125-133 means)
  * Rg may be NULL when only Euler angles are wanted; all outputs nullable. */
+#define SUHPE_EULER_DAD 2
 int suhpe_so3_metrics_f32(const float* Rp, const float* Rg, const float* gt_euler_deg, int64_t n,
                           int32_t full_range, float* geo_deg, float* frob, float* euler,
                           float* abs_err, float* mae, double* sums, int* status, void* stream);

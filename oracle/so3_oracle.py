@@ -521,6 +521,29 @@ def euler_from_matrices(R, full_range=False):
                         z * keep + zs * singular), dim=1)
 
 
+def rotate_aug_adjust(pred_weak, aug_rot_mat, train_labeled):
+    """src/agent.py:110-119, the same torch ops in the same order."""
+    mat = pred_weak.clone().view(-1, 3, 3)
+    if train_labeled == "DAD3DHeads":
+        return torch.matmul(aug_rot_mat, mat).view(-1, 9)
+    rot_180 = torch.tensor([[1, 0, 0], [0, -1, 0], [0, 0, -1]], dtype=pred_weak.dtype)
+    trans = torch.matmul(rot_180, mat.transpose(1, 2))
+    trans = torch.matmul(aug_rot_mat, trans)
+    return torch.matmul(rot_180, trans).transpose(1, 2).reshape(-1, 9)
+
+
+def euler_dad_degrees(R):
+    """(b,3,3) -> (b,3) float64 degrees (pitch, yaw, roll) of a DAD-trained model: the per-sample
+    loop of eval.py:66-74 (scipy ``as_euler("xyz")`` of the transpose, then ``limit_angle``)."""
+    from scipy.spatial.transform import Rotation
+    out = []
+    for rot_mat in R.detach().cpu().numpy():
+        angle = Rotation.from_matrix(np.transpose(rot_mat)).as_euler("xyz", degrees=True)
+        roll, pitch, yaw = list(map(limit_angle, [angle[2], angle[0] - 180, angle[1]]))
+        out.append([pitch, yaw, roll])
+    return np.array(out)
+
+
 def geodesic_deg(pred, gt):
     """rad2deg(so3_relative_angle)  (src/agent.py:449-451, eval.py:88-89)."""
     return torch.rad2deg(p3d.so3_relative_angle(pred, gt))

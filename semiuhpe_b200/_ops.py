@@ -92,6 +92,19 @@ def fisher_ce(A1, A2, *, grad=False):
     return out
 
 
+def rotate_adjust(pred, aug_rot, mode):
+    """(n,9) teacher parameters moved into the rotate-augmented view (src/agent.py:110-119)."""
+    P9, R9 = as_records(pred, "pred_weak"), as_records(aug_rot, "aug_rot_mat")
+    n = P9.shape[0]
+    if R9.shape[0] != n:
+        raise RuntimeError(f"shape mismatch: pred_weak has {n} matrices, aug_rot_mat has {R9.shape[0]}")
+    out = torch.empty((n, 9), dtype=torch.float32, device=P9.device)
+    if n:
+        with torch.cuda.device(P9.device):
+            check(lib().suhpe_rotate_adjust_f32(ptr(P9), ptr(R9), n, int(mode), ptr(out), stream()), "rotate_adjust")
+    return out
+
+
 def fisher_from_s(S, *, logC=True, G=False, entropy=False):
     """K2 on given singular values (logC_F)."""
     S3 = as_records(S, "S", 3)
@@ -177,7 +190,8 @@ def so3_metrics(Rp, Rg=None, gt_euler=None, *, full_range=False, geo=False, frob
         return out
     status = _status_word(dev)
     with torch.cuda.device(dev):
-        check(lib().suhpe_so3_metrics_f32(ptr(P9), ptr(G9), ptr(E3), n, int(bool(full_range)),
+        mode = 2 if full_range == "dad" else int(bool(full_range))
+        check(lib().suhpe_so3_metrics_f32(ptr(P9), ptr(G9), ptr(E3), n, mode,
                                           ptr(out.get("geo")), ptr(out.get("frob")), ptr(out.get("euler")),
                                           ptr(out.get("abs_err")), ptr(out.get("mae")), ptr(out.get("sums")),
                                           ptr(status), stream()), "so3_metrics")

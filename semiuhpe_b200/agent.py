@@ -85,6 +85,15 @@ def compute_dynamic_entropy_threshold(agent, ulb_train_bar):
 
 
 # ------------------------------------------------------------ a13..a16: metrics
+def rotate_aug_adjust(pred_weak, aug_rot_mat, train_labeled):
+    """``pred_weak_adjusted`` of src/agent.py:110-122: the teacher's (b,9) parameters expressed in the
+    frame of the rotate-augmented strong view.  ``train_labeled``: "DAD3DHeads" (left product with the
+    augmentation rotation) or "300WLP" (the transposed convention, conjugated by Rx(180))."""
+    if train_labeled not in ("DAD3DHeads", "300WLP"):
+        raise ValueError(f"rotate_aug_adjust: unknown train_labeled {train_labeled!r}")
+    return _ops.rotate_adjust(pred_weak, aug_rot_mat, 0 if train_labeled == "DAD3DHeads" else 1)
+
+
 def compute_err_deg_from_matrices(pred, gt, gt_euler=None):
     """(b,3,3),(b,3,3)[,(b,3) degrees] -> (b,) error in degrees (src/agent.py:447-455):
     geodesic angle via pytorch3d's ``so3_relative_angle`` semantics when ``gt_euler`` is
@@ -108,15 +117,17 @@ def _quat_to_matrix(q):
     return o.reshape(q.shape[:-1] + (3, 3))
 
 
-def eval_rotation_metrics(pred, gt, gt_euler=None):
+def eval_rotation_metrics(pred, gt, gt_euler=None, dad_trained=False):
     """One K4 launch for the evaluation loop of eval.py:76-98,125-133.
 
     With ``gt_euler`` (degrees): per-angle absolute errors (n,3) and their means
     ``(pitch, yaw, roll, mean)``; without: geodesic degrees (n,), Frobenius distance
-    (n,) and their means.  Means are accumulated in fp64 on the device."""
+    (n,) and their means.  Means are accumulated in fp64 on the device.  ``dad_trained`` selects
+    the Euler convention of models trained on DAD-3DHeads (eval.py:60-74, ``config.train_labeled``)."""
     n = pred.reshape(-1, 9).shape[0]
     if gt_euler is not None:
-        out = _ops.so3_metrics(pred, gt, gt_euler, full_range=False, abs_err=True, mae=True, sums=True)
+        out = _ops.so3_metrics(pred, gt, gt_euler, full_range="dad" if dad_trained else False,
+                               abs_err=True, mae=True, sums=True)
         s = out["sums"] / max(n, 1)
         return dict(abs_err=out["abs_err"], mae=out["mae"], pitch=s[2], yaw=s[3], roll=s[4], mean=s[5])
     out = _ops.so3_metrics(pred, gt, geo=True, frob=True, sums=True)

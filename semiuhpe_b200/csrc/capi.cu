@@ -248,6 +248,11 @@ int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, 
     return rc(launch_fisher_ce_close(c, st(stream)));
 }
 
+int suhpe_rotate_adjust_f32(const float* pred, const float* aug_rot, int64_t n, int32_t mode, float* out, void* stream) {
+    if (n < 0 || mode < 0 || mode > 1 || (n > 0 && (!pred || !aug_rot || !out))) return SUHPE_EINVAL;
+    return rc(launch_rotate_adjust(pred, aug_rot, (long long)n, (int)mode, out, st(stream)));
+}
+
 int suhpe_laplace_nll_f32(const float* A, const float* Rgt, int64_t n, const float* grid, int32_t N,
                           float* nll, float* grad, float* mode, float* logF, int* status, void* stream) {
     if (n < 0 || N <= 0 || (n > 0 && (!A || !Rgt || !grid || !nll))) return SUHPE_EINVAL;

@@ -530,6 +530,58 @@ fisher_ce_close_kernel(FisherCeArgs p, bool vec_ok) {
 }
 
 // ---------------------------------------------------------------------------
+// Rotate-augmentation adjustment of the teacher's parameter matrices (src/agent.py:110-119, SURVEY
+// 8f-2): the unlabeled image was rotated in-plane for the strong view, so the weak-view prediction
+// is moved into the strong view's frame before it becomes the pseudo label.
+//   mode 0 (train_labeled == "DAD3DHeads"):  out = Raug P
+//   mode 1 (train_labeled == "300WLP"):      out = (D Raug D P^T)^T = P D Raug^T D,  D = diag(1,-1,-1)
+// Thread per matrix, tiles staged like K1.  HBM-bound, 108 B per matrix.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSvdThreads)
+rotate_adjust_kernel(const float* __restrict__ P, const float* __restrict__ Raug, long long n, int mode,
+                     float* __restrict__ out, bool vec_ok) {
+    __shared__ SvdScratch scratch[kSvdWarps];        // a: P in -> result out, r: Raug in
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    SvdScratch& ws = scratch[warp];
+    const long long warps_total = (long long)gridDim.x * kSvdWarps;
+    const long long tiles = (n + 31) / 32;
+    for (long long tile = (long long)blockIdx.x * kSvdWarps + warp; tile < tiles; tile += warps_total) {
+        const long long base = tile * 32;
+        const int count = (int)min(32LL, n - base);
+        load_tile(ws.a, P + base * 9, count, vec_ok, lane);
+        load_tile(ws.r, Raug + base * 9, count, vec_ok, lane);
+        __syncwarp();
+        float M[9];
+        if (lane < count) {
+            float p[9], r[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { p[k] = ws.a[lane * 9 + k]; r[k] = ws.r[lane * 9 + k]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (mode == 0) {
+                        M[3 * i + j] = fmaf(r[3 * i], p[j], fmaf(r[3 * i + 1], p[3 + j], r[3 * i + 2] * p[6 + j]));
+                    } else {
+                        // (P D Raug^T D)_ij = sum_k P_ik d_k d_j Raug_jk
+                        const float dj = (j == 0) ? 1.0f : -1.0f;
+                        M[3 * i + j] = fmaf(p[3 * i], dj * r[3 * j], fmaf(p[3 * i + 1], -dj * r[3 * j + 1], p[3 * i + 2] * (-dj * r[3 * j + 2])));
+                    }
+                }
+        }
+        __syncwarp();
+        if (lane < count) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) ws.a[lane * 9 + k] = M[k];
+        }
+        __syncwarp();
+        store_tile(out + base * 9, ws.a, count, vec_ok, lane);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Body probe (bench/profiling aid): the W2 pass body of one run type in a tight loop, tables in
 // shared memory, no per-sample glue.  variant bits: 0-1 type, 2 skip LDS, 3 skip MUFU, 4 skip mask
 // ---------------------------------------------------------------------------
@@ -672,6 +724,17 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     // first radix-select pass over the entropies just written (they are still L2-resident)
     if (err == cudaSuccess && p.hist) err = launch_select_hist_accumulate(p.entropy, p.n, p.hist, stream);
     return err;
+}
+
+cudaError_t launch_rotate_adjust(const float* P, const float* Raug, long long n, int mode, float* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int sms = sm_count();
+    const long long tiles = (n + 31) / 32;
+    long long blocks = (tiles + kSvdWarps - 1) / kSvdWarps;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    rotate_adjust_kernel<<<(unsigned)blocks, kSvdThreads, 0, stream>>>(P, Raug, n, mode, out, aligned(P) && aligned(Raug) && aligned(out));
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream) {

@@ -62,7 +62,7 @@ struct MetricsArgs {
     const float* Rg;       // (n,9) ground truth | nullptr (Euler of Rp only)
     const float* gt_euler; // (n,3) degrees (pitch,yaw,roll) | nullptr
     long long n;
-    int full_range;
+    int full_range;        // 0 | 1: src/utils.py:232 (radians); 2: DAD-trained scipy-xyz convention (degrees, limit_angle)
     float* geo_deg;        // (n)   | nullptr
     float* frob;           // (n)   | nullptr
     float* euler;          // (n,3) radians | nullptr
@@ -89,6 +89,7 @@ struct FisherCeArgs {
 cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream);
 cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream);
 cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream);
+cudaError_t launch_rotate_adjust(const float* P, const float* Raug, long long n, int mode, float* out, cudaStream_t stream);
 cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream);
 cudaError_t launch_metrics(MetricsArgs p, cudaStream_t stream);
 

@@ -139,13 +139,15 @@ metrics_kernel(MetricsArgs p, bool vec_ok) {
             }
             if (want_euler) {
                 float e[3];
-                euler_from_rotation(Rp, p.full_range != 0, e);
+                const bool dad = p.full_range == 2;          // DAD convention: e is already in degrees
+                if (dad) euler_dad_degrees(Rp, e);
+                else euler_from_rotation(Rp, p.full_range != 0, e);
                 ws.eul[lane * 3] = e[0]; ws.eul[lane * 3 + 1] = e[1]; ws.eul[lane * 3 + 2] = e[2];
                 if (p.gt_euler) {
                     float d[3], sum = 0.0f;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        d[k] = fabsf(rad_to_deg_ref(e[k]) - st.ge[lane * 3 + k]);
+                        d[k] = fabsf((dad ? e[k] : rad_to_deg_ref(e[k])) - st.ge[lane * 3 + k]);
                         sum = add_rn(sum, d[k]);
                         acc[2 + k] += (double)d[k];
                     }

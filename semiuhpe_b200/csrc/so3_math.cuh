@@ -860,6 +860,36 @@ SUHPE_HD void euler_from_rotation(const float* R, bool full_range, float* out) {
     }
 }
 
+// limit_angle of DAD-3DHeads (src/utils.py:289-300): wrap degrees into [-180, 180] with the
+// reference's int() (truncation) and // (floor) arithmetic.
+SUHPE_HD float limit_angle_deg(float a) {
+    if (a < -180.0f) a = fmaf(-2.0f * floorf(truncf(a / 180.0f) * 0.5f), 180.0f, a);
+    if (a > 180.0f) a = fmaf(-2.0f * floorf((truncf(a / 180.0f) + 1.0f) * 0.5f), 180.0f, a);
+    return a;
+}
+
+// DAD-trained models (eval.py:66-74, predict.py:84-87, image.py:218-221): the angles are
+// scipy's Rotation.from_matrix(R^T).as_euler("xyz", degrees=True) = (a0, a1, a2) with
+// R^T = Rz(a2) Ry(a1) Rx(a0), then [roll, pitch, yaw] = limit_angle([a2, a0 - 180, a1]); returned
+// in the reference's list order (pitch, yaw, roll), DEGREES.  At gimbal lock (|R02| = 1) scipy
+// zeroes the third angle and puts the whole in-plane rotation into the first.
+SUHPE_HD void euler_dad_degrees(const float* R, float* out) {
+    const float kDeg = 57.29577951308232f;
+    const float cy = sqrt_rn(fmaf(R[0], R[0], R[1] * R[1]));         // cos(a1) >= 0
+    const float a1 = atan2_so3(-R[2], cy);
+    float a0, a2;
+    if (cy > 1e-6f) {
+        a0 = atan2_so3(R[5], R[8]);
+        a2 = atan2_so3(R[1], R[0]);
+    } else {                                                          // gimbal lock: a2 := 0
+        a0 = atan2_so3(-R[7], R[4]);
+        a2 = 0.0f;
+    }
+    out[0] = limit_angle_deg(fmaf(a0, kDeg, -180.0f));
+    out[1] = limit_angle_deg(a1 * kDeg);
+    out[2] = limit_angle_deg(a2 * kDeg);
+}
+
 // mean_3 | euler * 180 / pi - gt_euler_deg |   (src/agent.py:452-454)
 SUHPE_HD float euler_mae_degrees(const float* euler_rad, const float* gt_deg) {
     float acc = 0.0f;

@@ -18,6 +18,14 @@ def compute_euler_angles_from_rotation_matrices(rotation_matrices, full_range=Fa
     return _ops.so3_metrics(R, full_range=full_range, euler=True)["euler"]
 
 
+def euler_dad_degrees(rotation_matrices):
+    """(b,3,3) -> (b,3) DEGREES (pitch, yaw, roll) in the convention of models trained on
+    DAD-3DHeads: per sample ``Rotation.from_matrix(R.T).as_euler("xyz", degrees=True)`` and
+    ``[roll, pitch, yaw] = limit_angle([a2, a0 - 180, a1])`` -- eval.py:66-74, predict.py:84-87,
+    image.py:218-221 (a scipy call per sample on the host in the reference; one K4 launch here)."""
+    return _ops.so3_metrics(rotation_matrices, full_range="dad", euler=True)["euler"]
+
+
 def get_6DRepNet_Rot(x, y, z):
     """R = Rz(z) Ry(y) Rx(x) from radians (host helper used to build labels, src/utils.py:204-226)."""
     cx, sx, cy, sy, cz, sz = math.cos(x), math.sin(x), math.cos(y), math.sin(y), math.cos(z), math.sin(z)

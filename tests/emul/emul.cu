@@ -234,6 +234,10 @@ void emul_metrics(const float* Rp, const float* Rg, const float* gt_euler, long 
     }
 }
 
+void emul_euler_dad(const float* R, long n, float* out) {
+    for (long i = 0; i < n; ++i) euler_dad_degrees(R + 9 * i, out + 3 * i);
+}
+
 void emul_atan2(const float* y, const float* x, long n, float* out) {
     for (long i = 0; i < n; ++i) out[i] = atan2_so3(y[i], x[i]);
 }

@@ -23,6 +23,7 @@ fisher_ce.npz  fisher_CE(A1 target, A2 prediction) and its autograd gradient w.r
              (src/fisher/fisher_utils.py:84-99; quaternion frames through the restated
              pytorch3d matrix_to_quaternion -- the value and the gradient do not depend on its
              branch or sign choices), plus fp64 anchors from the oracle's restatement
+dad_euler.npz  the DAD-trained Euler convention of eval.py:66-74 (scipy as_euler + limit_angle)
 metrics.npz  compute_euler_angles_from_rotation_matrices (src/utils.py:232),
              compute_err_deg_from_matrices (src/agent.py:447-455, extracted by AST),
              so3_relative_angle via the restated pytorch3d (PARITY UNPINNED for that
@@ -253,9 +254,36 @@ def make_metrics(ref):
     print("metrics.npz", n, "pairs")
 
 
+def make_dad_euler(ref):
+    """eval.py:66-74 executed literally (scipy + the reference's limit_angle) on full-range rotations,
+    near-frontal heads of a DAD-trained model (pitch offset by 180) and the gimbal-lock poses."""
+    from scipy.spatial.transform import Rotation
+    gen = torch.Generator().manual_seed(4242)
+    R = random_rotations(2048, gen)
+    ang = (torch.rand(1024, 3, generator=gen) * 2 - 1) * torch.tensor([60.0, 80.0, 50.0])
+    rx180 = torch.diag(torch.tensor([1.0, -1.0, -1.0]))
+    near = torch.stack([torch.from_numpy(ref.get_6DRepNet_Rot(*np.deg2rad(a.numpy()))).float() for a in ang])
+    near = (near @ rx180).transpose(1, 2).contiguous()
+    lock = torch.stack([torch.from_numpy(Rotation.from_euler("xyz", [t, s * 90.0, 20.0], degrees=True).as_matrix().T).float()
+                        for t in (-170.0, -30.0, 0.0, 45.0, 120.0) for s in (-1.0, 1.0)])
+    Rall = torch.cat((R, near, lock)).contiguous()
+    import warnings
+    rows = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                    # scipy warns at gimbal lock
+        for rot_mat in Rall.numpy():
+            rot_mat_2 = np.transpose(rot_mat)
+            angle = Rotation.from_matrix(rot_mat_2).as_euler("xyz", degrees=True)
+            roll, pitch, yaw = list(map(ref.limit_angle, [angle[2], angle[0] - 180, angle[1]]))
+            rows.append([pitch, yaw, roll])
+    names = np.array(["random"] * 2048 + ["near_frontal"] * 1024 + ["gimbal_lock"] * len(lock))
+    np.savez_compressed(os.path.join(HERE, "dad_euler.npz"), R=Rall.numpy(), euler_deg=np.array(rows), names=names)
+    print("dad_euler.npz", len(Rall), "rotations")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixed reduction order inside the reference's torch ops
     ref = ref_shim.load()
-    makers = dict(fisher=make_fisher, fisher_ce=make_fisher_ce, laplace=make_laplace, select=make_select, metrics=make_metrics)
+    makers = dict(fisher=make_fisher, fisher_ce=make_fisher_ce, dad_euler=make_dad_euler, laplace=make_laplace, select=make_select, metrics=make_metrics)
     for name in (sys.argv[1:] or list(makers)):          # `make_golden.py fisher_ce` regenerates one file
         makers[name](ref)

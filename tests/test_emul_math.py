@@ -265,3 +265,21 @@ def test_fisher_ce_against_golden(emul, golden):
     assert (err64[stable] <= np.maximum(2 * ref_err64[stable], 2e-5)).all()
     # near-degenerate students: 1/(s_i - s_j) amplifies fp32 rounding sample by sample; compare the class
     assert err64[~stable].max() <= max(2 * ref_err64[~stable].max(), 1e-4)
+
+
+def angle_diff_deg(a, b):
+    d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    return np.minimum(d, np.abs(d - 360.0))
+
+
+def test_dad_euler_against_golden(emul, golden):
+    """DAD-trained Euler convention (eval.py:66-74: scipy as_euler("xyz") of R^T + limit_angle),
+    fixture generated by executing those lines; fp32 rotations against scipy's float64."""
+    g = golden("dad_euler")
+    R = np.ascontiguousarray(g["R"].reshape(-1, 9))
+    out = np.zeros((len(R), 3), np.float32)
+    emul.emul_euler_dad(P(R), ctypes.c_long(len(R)), P(out))
+    assert angle_diff_deg(out, g["euler_deg"]).max() < 1e-3
+    near = g["names"] == "near_frontal"
+    assert angle_diff_deg(out[near], g["euler_deg"][near]).max() < 1e-4
+    assert np.abs(out).max() <= 180.0

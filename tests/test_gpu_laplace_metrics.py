@@ -136,3 +136,24 @@ def test_metrics_full_size_properties(cuda):
     geo = _ops.so3_metrics(R2, R, geo=True, frob=True)
     assert (geo["geo"] - theta).abs().max().item() < 5e-3
     assert (geo["frob"] - 2 * (2 ** 0.5) * (t / 2).sin()).abs().max().item() < 1e-5
+
+
+def test_dad_euler_convention(cuda, golden):
+    """K4 mode 2 (eval.py:66-74): Euler angles of a DAD-trained model in degrees, the per-angle errors
+    and their means against the scipy-generated fixture."""
+    from semiuhpe_b200.agent import eval_rotation_metrics
+    from semiuhpe_b200.utils import euler_dad_degrees
+    g = golden("dad_euler")
+    R = torch.from_numpy(g["R"]).to(cuda)
+    ours = euler_dad_degrees(R).cpu().numpy()
+    d = np.abs(ours.astype(np.float64) - g["euler_deg"])
+    d = np.minimum(d, np.abs(d - 360.0))
+    assert d.max() < 1e-3
+    assert d[g["names"] == "near_frontal"].max() < 1e-4
+    keep = g["names"] == "near_frontal"                       # away from the +-180 wrap: errors are plain differences
+    gen = torch.Generator().manual_seed(1)
+    gt = torch.from_numpy(g["euler_deg"][keep]).float() + 3 * torch.randn(int(keep.sum()), 3, generator=gen)
+    ev = eval_rotation_metrics(R[torch.from_numpy(keep).to(cuda)], None, gt.to(cuda), dad_trained=True)
+    ref_err = np.abs(gt.numpy().astype(np.float64) - g["euler_deg"][keep])
+    np.testing.assert_allclose(ev["abs_err"].cpu().numpy(), ref_err, rtol=0, atol=2e-4)
+    np.testing.assert_allclose([ev["pitch"].item(), ev["yaw"].item(), ev["roll"].item()], ref_err.mean(0), rtol=1e-5)

@@ -50,3 +50,20 @@ def test_two_phase_pipeline_matches_single_call(cuda):
             assert torch.equal(one[key], two[key]), key
         assert one["threshold"] == two["threshold"] and one["kept"] == two["kept"]
     pipe.close()
+
+
+@pytest.mark.parametrize("n", [1, 33, 4097])
+@pytest.mark.parametrize("dataset", ["DAD3DHeads", "300WLP"])
+def test_rotate_aug_adjust(cuda, n, dataset):
+    """src/agent.py:110-119: exact up to the rounding of a 3-term dot product."""
+    from oracle import so3_oracle as orc
+    from semiuhpe_b200.agent import rotate_aug_adjust
+    gen = torch.Generator().manual_seed(n)
+    P = 10 * torch.randn(n, 9, generator=gen)
+    Raug = random_rotations(n, gen)
+    ours = rotate_aug_adjust(P.to(cuda), Raug.to(cuda), dataset).cpu()
+    ref = orc.rotate_aug_adjust(P.double(), Raug.double(), dataset)
+    assert ours.shape == (n, 9)
+    np.testing.assert_allclose(ours.numpy(), ref.numpy(), rtol=0, atol=4e-6)
+    with pytest.raises(ValueError):
+        rotate_aug_adjust(P.to(cuda), Raug.to(cuda), "BIWI")

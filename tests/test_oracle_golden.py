@@ -78,6 +78,14 @@ def test_fisher_ce_golden(golden):
     np.testing.assert_allclose(same.numpy(), orc.fisher_entropy(A1[:64]).numpy(), rtol=1e-5, atol=2e-5)
 
 
+def test_dad_euler_golden(golden):
+    g = golden("dad_euler")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.testing.assert_allclose(orc.euler_dad_degrees(torch.from_numpy(g["R"])), g["euler_deg"], rtol=0, atol=1e-9)
+
+
 def test_laplace_golden(golden):
     g = golden("laplace")
     A, R, grids = (torch.from_numpy(g[k]) for k in ("A", "R", "grids"))
