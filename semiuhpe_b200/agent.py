@@ -84,6 +84,51 @@ def compute_dynamic_entropy_threshold(agent, ulb_train_bar):
     return thr
 
 
+# --------------------------------------------------- 8f-3: the unsupervised branch, sync-free
+def unsupervised_terms(pred_weak, pred_strong, conf_thres, *, type_unsuper="ce", distribution="matrixFisher",
+                       grids=None, aug_rot_mat=None, train_labeled="300WLP", ulb_gt=None, overreg=1.025):
+    """The unsupervised half of ``SSLAgent.forward`` (src/agent.py:99-192) without its host
+    synchronisations: the reference tests ``mask_ratio_fisher > 0`` on the host (:151) and gathers
+    ``pred[mask_fisher]`` (dynamic shapes, :152-160); here every sample goes through the loss
+    kernel and the mask enters as a weight -- ``mean(l[mask]) * mask_ratio == sum(where(mask, l, 0)) / b``,
+    with the same gradients (zero for filtered samples) -- so the step is a fixed launch sequence
+    (CUDA-graph capturable with ``semiuhpe_b200.set_error_checking(False)``).
+
+    pred_weak: teacher output (b,9) (detached like :107); pred_strong: student output (b,9);
+    conf_thres: float or the SelectWorkspace of :func:`entropy_threshold` (``sync=False``).
+    Returns device tensors: unsuper_loss (scalar, already multiplied by the mask ratio like :166),
+    entropy (b,), mask (b,) bool, mask_ratio, and the three error terms of :169-180 as per-sample
+    vectors over the WHOLE batch plus their masked means (the reference returns the masked subsets)."""
+    from .fisher.fisher_utils import batch_torch_A_to_R, fisher_CE, vmf_loss
+    pred_weak = pred_weak.detach()
+    b = pred_weak.reshape(-1, 9).shape[0]
+    entropy = fisher_entropy(pred_weak)                                   # :139 (not rotate-adjusted)
+    mask, mask_ratio = entropy_mask(entropy, conf_thres)                  # :148-150
+    adjusted = pred_weak.reshape(-1, 9) if aug_rot_mat is None else rotate_aug_adjust(pred_weak, aug_rot_mat, train_labeled)
+    pseudo = batch_torch_A_to_R(adjusted)                                 # :152
+    if type_unsuper == "ce":                                              # :155,160 (both distributions)
+        losses = fisher_CE(adjusted, pred_strong)
+    elif type_unsuper == "nll" and distribution == "matrixFisher":        # :157
+        losses, _ = vmf_loss(pred_strong, pseudo, overreg=overreg)
+    elif type_unsuper == "nll" and distribution == "RotationLaplace":     # :162
+        from .laplace.rotation_laplace import NLL_loss
+        losses, _ = NLL_loss("RLaplace", pred_strong, pseudo, grids)
+    else:
+        raise ValueError(f"unsupervised_terms: unknown loss {type_unsuper!r} / distribution {distribution!r}")
+    zero = torch.zeros((), dtype=losses.dtype, device=losses.device)
+    unsuper_loss = torch.where(mask, losses, zero).sum() / b              # == mean(l[mask]) * mask_ratio  (:163,166)
+    out = dict(unsuper_loss=unsuper_loss, entropy=entropy, mask=mask, mask_ratio=mask_ratio)
+    kept = mask.sum().clamp(min=1)
+    masked_mean = lambda v: torch.where(mask, v, zero).sum() / kept
+    strong_rot = batch_torch_A_to_R(pred_strong.detach())
+    out["err_strongSuper_pseudo"] = compute_err_deg_from_matrices(strong_rot, pseudo)      # :177-180
+    out["err_strongSuper_pseudo_mean"] = masked_mean(out["err_strongSuper_pseudo"])
+    if ulb_gt is not None:                                                # :169-172
+        out["err_weakAll_gt"] = compute_err_deg_from_matrices(pseudo, ulb_gt)
+        out["err_weakPseudo_gt_mean"] = masked_mean(out["err_weakAll_gt"])
+    return out
+
+
 # ------------------------------------------------------------ a13..a16: metrics
 def rotate_aug_adjust(pred_weak, aug_rot_mat, train_labeled):
     """``pred_weak_adjusted`` of src/agent.py:110-122: the teacher's (b,9) parameters expressed in the
