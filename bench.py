@@ -198,6 +198,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner (and anything NCCL_DEBUG asks for) on stdout by default:
+        # keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         graft.build()
@@ -468,7 +471,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
-    ap.add_argument("--e2e-chunk", type=int, default=1 << 20, help="pairs per chunk of the host-buffer pipeline")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 19, help="pairs per chunk of the host-buffer pipeline")
     ap.add_argument("--skip-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
