@@ -445,8 +445,24 @@ def side_configs(torch, dev, _ops):
         c1()
         dynamic_entropy_filter(A128, LEFT_RATIO, return_threshold=False)
 
+    def c2_ssl():
+        # the whole SSL step of BASELINE config 2 with the default unsupervised loss (type_unsuper 'ce'):
+        # supervised NLL fwd+bwd on 32 + entropy/mask/fisher_CE fwd+bwd on 128, no host sync
+        from semiuhpe_b200.agent import unsupervised_terms
+        c1()
+        strong = (A128 + 0.5).requires_grad_(True)
+        unsupervised_terms(A128, strong, -3.6, type_unsuper="ce")["unsuper_loss"].backward()
+
     out["c1_fisher_b32_fwd_bwd_us"] = 1e3 * timed(c1, 50)
     out["c2_teacher_step_32_128_us"] = 1e3 * timed(c2, 50)
+    out["c2_ssl_step_ce_32_128_us"] = 1e3 * timed(c2_ssl, 50)
+    nce = 1 << 22
+    Ace1 = 10 * torch.randn(nce, 9, device=dev, generator=gen)
+    Ace2 = Ace1 + 2 * torch.randn(nce, 9, device=dev, generator=gen)
+    ms = timed(lambda: _ops.fisher_ce(Ace1, Ace2, grad=True), 3)
+    out["fisher_ce_2p22_fwd_bwd_ms"] = ms
+    out["fisher_ce_pairs_per_s"] = nce / (ms * 1e-3)
+    del Ace1, Ace2
     n3, N = 1 << 20, 4608
     grid = rot(N)
     A3, R3 = 5 * torch.randn(n3, 9, device=dev, generator=gen), rot(n3)

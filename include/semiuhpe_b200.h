@@ -77,6 +77,12 @@ int suhpe_set_quadrature_cut_bits(int bits);
 #define SUHPE_FISHER_CE_WORKSPACE_FLOATS 10
 int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
                         float* workspace, int* status, void* stream);
+/* Same, with G1 = d logC / dS of the target (n,3) supplied by the caller: the training step has
+ * it already -- the entropy launch on the teacher output (suhpe_fisher_fused_f32 with G) produced
+ * it, and the rotate-augmentation adjustment (a rotation applied on one side) leaves the singular
+ * values, hence G1, unchanged -- so the cross entropy costs one quadrature instead of two. */
+int suhpe_fisher_ce_with_g1_f32(const float* A1, const float* G1, const float* A2, int64_t n, float* ce,
+                                float* gradA2, float* workspace, int* status, void* stream);
 
 /* Rotate-augmentation adjustment of the teacher's parameter matrices before they become pseudo
  * labels (src/agent.py:110-119): mode 0 (train_labeled "DAD3DHeads") out = aug_rot * pred;

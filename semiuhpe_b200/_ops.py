@@ -72,8 +72,9 @@ def fisher_fused(A, R=None, overreg=1.0, *, nll=False, grad=False, rot=False, en
     return out
 
 
-def fisher_ce(A1, A2, *, grad=False):
-    """fisher_CE value (n,) and, on request, d ce_i / d A2_i (n,9): two K2 launches + the closing kernel."""
+def fisher_ce(A1, A2, *, grad=False, target_G=None):
+    """fisher_CE value (n,) and, on request, d ce_i / d A2_i (n,9): two K2 launches + the closing kernel
+    (one K2 launch when ``target_G`` = d logC/dS of the target (n,3) is supplied)."""
     T9, P9 = as_records(A1, "A1"), as_records(A2, "A2")
     n = P9.shape[0]
     if T9.shape[0] != n:
@@ -86,8 +87,15 @@ def fisher_ce(A1, A2, *, grad=False):
     work = torch.empty(_capi.FISHER_CE_WORKSPACE_FLOATS * n, dtype=torch.float32, device=dev)
     status = _status_word(dev)
     with torch.cuda.device(dev):
-        check(lib().suhpe_fisher_ce_f32(ptr(T9), ptr(P9), n, ptr(out["ce"]), ptr(out.get("grad")), ptr(work),
-                                        ptr(status), stream()), "fisher_CE")
+        if target_G is None:
+            check(lib().suhpe_fisher_ce_f32(ptr(T9), ptr(P9), n, ptr(out["ce"]), ptr(out.get("grad")), ptr(work),
+                                            ptr(status), stream()), "fisher_CE")
+        else:
+            G3 = as_records(target_G, "target_G", 3)
+            if G3.shape[0] != n:
+                raise RuntimeError(f"shape mismatch: target_G has {G3.shape[0]} rows, A2 has {n}")
+            check(lib().suhpe_fisher_ce_with_g1_f32(ptr(T9), ptr(G3), ptr(P9), n, ptr(out["ce"]), ptr(out.get("grad")),
+                                                    ptr(work), ptr(status), stream()), "fisher_CE")
     _raise_from_status(status, "fisher_CE")
     return out
 

@@ -102,12 +102,15 @@ def unsupervised_terms(pred_weak, pred_strong, conf_thres, *, type_unsuper="ce",
     from .fisher.fisher_utils import batch_torch_A_to_R, fisher_CE, vmf_loss
     pred_weak = pred_weak.detach()
     b = pred_weak.reshape(-1, 9).shape[0]
-    entropy = fisher_entropy(pred_weak)                                   # :139 (not rotate-adjusted)
+    # :139 (not rotate-adjusted); the same launch yields g = d logC/dS of the teacher, which fisher_CE
+    # needs for the target and which the adjustment (a rotation on one side) does not change
+    stats = _ops.fisher_fused(pred_weak, None, 1.0, entropy=True, G=(type_unsuper == "ce"), what="fisher_entropy")
+    entropy = stats["entropy"]
     mask, mask_ratio = entropy_mask(entropy, conf_thres)                  # :148-150
     adjusted = pred_weak.reshape(-1, 9) if aug_rot_mat is None else rotate_aug_adjust(pred_weak, aug_rot_mat, train_labeled)
     pseudo = batch_torch_A_to_R(adjusted)                                 # :152
     if type_unsuper == "ce":                                              # :155,160 (both distributions)
-        losses = fisher_CE(adjusted, pred_strong)
+        losses = fisher_CE(adjusted, pred_strong, target_G=stats["G"])
     elif type_unsuper == "nll" and distribution == "matrixFisher":        # :157
         losses, _ = vmf_loss(pred_strong, pseudo, overreg=overreg)
     elif type_unsuper == "nll" and distribution == "RotationLaplace":     # :162

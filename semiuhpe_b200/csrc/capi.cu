@@ -228,24 +228,38 @@ int suhpe_fisher_from_s_f32(const float* S, int64_t n, float* logC, float* G, fl
     return rc(launch_fisher_fused(p, st(stream)));
 }
 
-int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
-                        float* workspace, int* status, void* stream) {
+static int fisher_ce_impl(const float* A1, const float* G1_given, const float* A2, int64_t n, float* ce, float* gradA2,
+                          float* workspace, int* status, void* stream) {
     if (n < 0 || (n > 0 && (!A1 || !A2 || !ce || !workspace))) return SUHPE_EINVAL;
     if (n == 0) return 0;
     float* G1 = workspace;                     // (n,3)
     float* S2 = workspace + 3 * n;             // (n,3)
     float* G2 = workspace + 6 * n;             // (n,3)
     float* H2 = workspace + 9 * n;             // (n)
-    FisherArgs t{};
-    t.A = A1; t.n = (long long)n; t.overreg = 1.0f; t.G = G1; t.status = status; t.cut_bits = g_cut_bits;
-    cudaError_t e = launch_fisher_fused(t, st(stream));
-    if (e != cudaSuccess) return rc(e);
+    cudaError_t e = cudaSuccess;
+    if (!G1_given) {
+        FisherArgs t{};
+        t.A = A1; t.n = (long long)n; t.overreg = 1.0f; t.G = G1; t.status = status; t.cut_bits = g_cut_bits;
+        e = launch_fisher_fused(t, st(stream));
+        if (e != cudaSuccess) return rc(e);
+    }
     FisherArgs q{};
     q.A = A2; q.n = (long long)n; q.overreg = 1.0f; q.S = S2; q.G = G2; q.entropy = H2; q.status = status; q.cut_bits = g_cut_bits;
     e = launch_fisher_fused(q, st(stream));
     if (e != cudaSuccess) return rc(e);
-    FisherCeArgs c{A1, A2, (long long)n, G1, S2, G2, H2, ce, gradA2, status};
+    FisherCeArgs c{A1, A2, (long long)n, G1_given ? G1_given : G1, S2, G2, H2, ce, gradA2, status};
     return rc(launch_fisher_ce_close(c, st(stream)));
+}
+
+int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
+                        float* workspace, int* status, void* stream) {
+    return fisher_ce_impl(A1, nullptr, A2, n, ce, gradA2, workspace, status, stream);
+}
+
+int suhpe_fisher_ce_with_g1_f32(const float* A1, const float* G1, const float* A2, int64_t n, float* ce, float* gradA2,
+                                float* workspace, int* status, void* stream) {
+    if (n > 0 && !G1) return SUHPE_EINVAL;
+    return fisher_ce_impl(A1, G1, A2, n, ce, gradA2, workspace, status, stream);
 }
 
 int suhpe_rotate_adjust_f32(const float* pred, const float* aug_rot, int64_t n, int32_t mode, float* out, void* stream) {

@@ -82,9 +82,9 @@ class _FisherCE(torch.autograd.Function):
     """ce_i and d ce_i / d A2_i from the same three launches."""
 
     @staticmethod
-    def forward(ctx, A1, A2):
+    def forward(ctx, A1, A2, target_G):
         need_grad = ctx.needs_input_grad[1]
-        out = _ops.fisher_ce(A1, A2, grad=need_grad)
+        out = _ops.fisher_ce(A1, A2, grad=need_grad, target_G=target_G)
         if need_grad:
             ctx.save_for_backward(out["grad"])
         ctx.a_shape = A2.shape
@@ -93,17 +93,20 @@ class _FisherCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_ce):
         (grad,) = ctx.saved_tensors
-        return None, (grad * g_ce.reshape(-1, 1)).view(ctx.a_shape)
+        return None, (grad * g_ce.reshape(-1, 1)).view(ctx.a_shape), None
 
 
-def fisher_CE(A1, A2):
+def fisher_CE(A1, A2, target_G=None):
     """Cross entropy h(f1, f2) of two matrix-Fisher densities, A1 the target and A2 the
     prediction, (b,9)|(b,3,3) x2 -> (b,)  -- reference fisher_utils.py:84-99 (the default
     unsupervised loss, src/agent.py:155).  Differentiable w.r.t. A2 like the reference (through the
     SVD, the quaternion frame and logC_F, here in closed form).  A1 is a constant: the agent feeds
     the detached teacher prediction (src/agent.py:107); asking for its gradient is an error rather
-    than a silent zero.  NaN/Inf results raise AssertionError as in the reference (:98)."""
+    than a silent zero.  NaN/Inf results raise AssertionError as in the reference (:98).
+    ``target_G`` (extension, optional): d logC/dS of the target, (b,3), e.g. the ``G`` output of the
+    entropy launch on the teacher prediction -- unchanged by the rotate-augmentation adjustment --
+    which saves the target's quadrature (one K2 launch instead of two)."""
     if isinstance(A1, torch.Tensor) and A1.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError("fisher_CE: the gradient w.r.t. the target A1 is not implemented "
                                   "(the reference's training loop detaches it, src/agent.py:107)")
-    return _FisherCE.apply(A1, A2)
+    return _FisherCE.apply(A1, A2, target_G)

@@ -60,6 +60,28 @@ def test_fisher_ce_ragged_and_layouts(cuda, n):
     assert torch.equal(off, ce.detach())
 
 
+def test_fisher_ce_with_supplied_target_statistics(cuda):
+    """target_G from the entropy launch on the UNADJUSTED teacher output equals what fisher_CE computes
+    itself for the rotate-adjusted target (singular values are invariant): same result, one K2 launch less."""
+    from semiuhpe_b200 import _ops
+    from semiuhpe_b200.agent import rotate_aug_adjust
+    from semiuhpe_b200.fisher.fisher_utils import fisher_CE
+    from helpers import random_rotations
+    gen = torch.Generator().manual_seed(2)
+    n = 5000
+    weak = (10 * torch.randn(n, 9, generator=gen)).to(cuda)
+    strong = (weak + 2 * torch.randn(n, 9, generator=gen).to(cuda)).requires_grad_(True)
+    adj = rotate_aug_adjust(weak, random_rotations(n, gen).to(cuda), "300WLP")
+    G = _ops.fisher_fused(weak, None, 1.0, entropy=True, G=True)["G"]
+    a = fisher_CE(adj, strong)
+    a.sum().backward()
+    ga = strong.grad.clone(); strong.grad = None
+    b = fisher_CE(adj, strong, target_G=G)
+    b.sum().backward()
+    assert torch.allclose(a, b, rtol=2e-6, atol=5e-6)
+    assert torch.allclose(ga, strong.grad, rtol=1e-5, atol=1e-6 * float(ga.abs().max()))
+
+
 def test_fisher_ce_errors(cuda):
     from semiuhpe_b200.fisher.fisher_utils import fisher_CE
     A = 5 * torch.randn(8, 9, device=cuda)
