@@ -16,6 +16,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # full capture of the dominant kernel
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fisher_fused -s 1 -c 2 -f -o $OUT/fisher_full \
     python profiles/run_kernels.py fisher 21 > $OUT/ncu_fisher.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'laplace|metrics|select|mask|hist' -c 12 -f -o $OUT/others_full \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'laplace|metrics|select|mask|hist|ce_close' -c 16 -f -o $OUT/others_full \
     python profiles/run_kernels.py others 21 > $OUT/ncu_others.log 2>&1
+timeout 300 python profiles/time_k4.py > $OUT/time_k4.log 2>&1
+timeout 300 python profiles/time_k2l.py > $OUT/time_k2l.log 2>&1
+timeout 300 python profiles/time_ce.py > $OUT/time_ce.log 2>&1
+cat $OUT/time_k4.log $OUT/time_k2l.log $OUT/time_ce.log
 tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; cat $OUT/bench.json; tail -3 $OUT/bench.err; cat $OUT/bench_ref.json

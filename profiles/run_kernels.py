@@ -28,6 +28,9 @@ for _ in range(1 if which == "others" else 3):
         m = min(n, 1 << 18)
         grid = rot(4608)
         _ops.laplace_nll(A[:m] * 0.5, R[:m], grid, grad=True, mode=True)
+    if which in ("ce", "others", "all"):
+        m = min(n, 1 << 20)
+        _ops.fisher_ce(A[:m], A[:m] + 2 * torch.randn(m, 9, device=dev, generator=gen), grad=True)
     if which in ("metrics", "others", "all"):
         ge = torch.rand(n, 3, device=dev, generator=gen) * 90
         _ops.so3_metrics(rot(n), R, ge, geo=True, frob=True, abs_err=True, sums=True)
