@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus, n_per_gpu):
@@ -198,9 +198,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner (and anything NCCL_DEBUG asks for) on stdout by default:
-        # keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         graft.build()
@@ -349,7 +346,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def fp32_probe(torch, lib, dev, _capi):
@@ -479,7 +476,27 @@ def side_configs(torch, dev, _ops):
     return out
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner
+    on stdout whenever NCCL_DEBUG is WARN or VERSION), so the real stdout is kept aside for the result
+    and file descriptor 1 is pointed at stderr for everything else in the process."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
