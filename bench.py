@@ -321,7 +321,7 @@ def run_ours(args):
                        "has no FP32-pipe figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
         "algorithmic_flop_per_rotation": FLOP_PER_ROTATION, "rotations_per_launch": n, "kernel_ms": fused_ms,
         "kernel_share_of_step": fused_ms / (ms_total / args.steps),
-        "traffic": None,
+        "traffic": k2_traffic(n),
         "hbm_view": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
                      "bytes_per_rotation": HBM_BYTES_PER_ROTATION,
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback"},
@@ -347,6 +347,19 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     emit(line)
+
+
+def k2_traffic(n):
+    """DRAM bytes of one K2 launch from the committed ncu capture (never measured in the timed run);
+    None when the capture was taken at another launch size."""
+    path = os.path.join(ROOT, "profiles", "r01_k2_traffic.json")
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path))
+    if t.get("rotations_per_launch") != n:
+        return None
+    return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes": t["algorithmic_bytes"],
+            "source": "profiles/r01_k2_traffic.json (ncu --set full, one launch)"}
 
 
 def fp32_probe(torch, lib, dev, _capi):

@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("SUHPE_NVCC_EXTRA", "").split()          # development A/B builds, e.g. -DSUHPE_K2_TREE_SUM=1
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
