@@ -420,22 +420,73 @@ SUHPE_HD int switch_index(float f, const float* t, bool falling) {
     return i;
 }
 
-// Negligible-node cut.  Every factor I0e(.) is <= 1, so y_i <= exp(-c u_i) for each of the
-// three families, while the normaliser sum is at least its last term,
-//   F >= 1/2 y0(x=1) = 1/2 I0e(s2+s3) >= 0.195 / sqrt(max(s2+s3, 1)).
-// Nodes with  c u_i >= ln 512 + bits ln 2 + ln(sqrt(max(s2+s3,1)) / 0.195)  therefore add up
-// to less than 2^-bits F over a whole family: with bits = 26 that is a quarter of an fp32 ulp
-// of F, i.e. below what the reference's own fp32 torch.sum resolves.  u falls with the node
-// index, so those nodes are a prefix [0,cut).  bits <= 0 disables the cut.
+// Negligible-node cut.  A prefix [0,cut) of a family's nodes is skipped when its whole trapezoid
+// mass is provably below 2^-bits of the normaliser sum F (bits = 26: an eighth of an fp32 ulp of F,
+// i.e. below what the reference's own fp32 torch.sum resolves).  u falls with the node index, so
+// "negligible" is a prefix.  Both sides of the comparison are bounded rigorously:
+//
+//   lower bound of F (family 0: fd0 = (s2-s3)/2, 2 fs0 = s2+s3, c0 = s1+s3).  I0e falls with its
+//   argument, so on the K+1 nodes next to x = 1 (u_k = k h, h = 2/511, k <= K)
+//       y0(u_k) >= I0e(s2+s3) I0e(fd0 K h) e^(-c0 h k)
+//   and with the trapezoid's half weight at k = 0
+//       F >= I0e_lo(s2+s3) I0e_lo(fd0 K h) (G_K - 1/2),  G_K = sum_{k<=K} e^(-c0 h k),
+//   I0e_lo(a) = max(e^-a, 0.39 / sqrt(max(a,1))) <= I0e(a);  K = floor(1/(c0 h)) (one e-folding), capped at 510.
+//
+//   upper bound of a prefix {i : u_i >= u*} of a family (fd, fs, c):  with I0e(a) <= min(1, kI0eUp/sqrt(a))
+//   (sup_a sqrt(a) I0e(a) = 0.4688), the d factor is <= Bd = I0e_up(fd u*) on the whole prefix; the s
+//   factor is <= 1 where v < v0 and <= Bs = I0e_up(fs v0) where v >= v0, for any split v0 -- taken at
+//   half the prefix, v0 = (2-u*)/2; and sum e^(-c u_i) over nodes with u_i >= w is a geometric series
+//   <= e^(-c w) / (1 - e^(-c h)).  Hence
+//       mass(prefix) <= Bd (Bs + e^(-c v0)) e^(-c u*) / (1 - e^(-c h)).
+//
+// A candidate u* is found by a few fixed-point steps and then CHECKED against the inequality (the
+// bound holds for any u*, however it was found); if the check fails the plain e^(-c u) bound
+// (Bd = Bs-term = 1) is used.  tests/test_emul_math.py verifies the claim in float64 over random
+// spectra.  bits <= 0 disables the cut.
+constexpr float kI0eUp = 0.4690f;
+constexpr float kQuadStep = (float)(2.0 / 511.0);
+
+SUHPE_HD float i0e_lower(float a) { return fmaxf(expf(-a), 0.39f / sqrt_rn(fmaxf(a, 1.0f))); }     // I0 >= 1 covers small a
+// ln of min(1, kI0eUp / sqrt(a))
+SUHPE_HD float ln_i0e_upper(float a) { return fminf(0.0f, -0.757153f - 0.5f * logf(fmaxf(a, 1e-30f))); }   // ln 0.4690 = -0.757153
+
+// ln(2^bits / F_lower) plus a little slack for the fp32 evaluation of the bound itself; +inf = no cut
 SUHPE_HD float cut_threshold(const float* s, int bits) {
     if (bits <= 0) return INFINITY;
-    const float m = fmaxf(s[1] + s[2], 1.0f);
-    return 6.2383246f + 0.69314718f * (float)bits + logf(sqrt_rn(m) * (1.0f / 0.195f)) + 0.01f;
+    const float c0 = s[0] + s[2], fd0 = fabsf(0.5f * (s[1] - s[2])), as0 = fabsf(s[1] + s[2]);
+    const float t = c0 * kQuadStep;
+    if (!(t >= 0.0f) || !(fabsf(s[0]) <= 3.0e38f) || !(as0 <= 3.0e38f) || !(fd0 <= 3.0e38f)) return INFINITY;   // NaN / inf spectra: evaluate everything
+    float K = 0.0f, G = 1.0f;
+    if (t < 1.0f) {
+        K = fminf(floorf(1.0f / fmaxf(t, 1e-9f)), 510.0f);
+        // exact geometric sum where 1 - e^-t is well conditioned, else the smallest term times the count
+        G = (t > 1e-3f) ? (1.0f - expf(-t * (K + 1.0f))) / (1.0f - expf(-t)) : (K + 1.0f) * expf(-t * K);
+    }
+    const float Flow = i0e_lower(as0) * i0e_lower(fd0 * K * kQuadStep) * (G - 0.5f);
+    return 0.69314718f * (float)bits - logf(Flow) + 0.02f;
 }
-SUHPE_HD int cut_index(float c, float thr) {
-    // first node that must be kept: u_i < thr / c  <=>  i > (2 - thr/c) * 255.5 ; one node of slack
-    const float lim = (2.0f - div_rn(thr, c)) * 255.5f - 1.0f;        // c <= 0 or thr = inf -> -inf/NaN -> 0
-    return (int)fminf(fmaxf(floorf(lim), 0.0f), (float)(kQuadNodes - 1));
+
+// ln of the prefix bound without its e^(-c u) / (1 - e^(-c h)) part: ln(Bd (Bs + e^(-c v0))), capped at 0
+SUHPE_HD float cut_prefix_factor(float fd, float fs, float c, float u) {
+    const float v0 = 0.5f * fmaxf(2.0f - u, 0.0f);
+    const float bs = expf(ln_i0e_upper(fs * v0)) + expf(-c * v0);
+    return ln_i0e_upper(fd * u) + fminf(0.0f, logf(bs));
+}
+
+SUHPE_HD int cut_index(float fd, float fs, float c, float thr) {
+    if (!(c > 0.0f) || !(thr < INFINITY)) return 0;
+    const float geo = -logf(1.0f - expf(-c * kQuadStep));          // c h -> 0: +inf -> no cut
+    const float rhs = thr + geo;
+    if (!(rhs < INFINITY)) return 0;
+    const float ic = div_rn(1.0f, c);
+    float u = 2.0f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) u = fminf(fmaxf((rhs + cut_prefix_factor(fd, fs, c, u)) * ic, 0.0f), 4.0f);
+    u += 2.0f * kQuadStep;                                           // safety margin before the check
+    if (!(fmaf(c, u, -cut_prefix_factor(fd, fs, c, u)) >= rhs)) u = rhs * ic;    // fall back to the plain bound
+    // nodes with u_i >= u:  i <= (2 - u) * 255.5 ; one more node of slack
+    const float lim = (2.0f - u) * 255.5f - 1.0f;
+    return (int)fminf(fmaxf(floorf(lim), 0.0f), (float)(kQuadNodes - 1));   // NaN -> 0
 }
 
 // (lo, hi, c) -> descriptor;  utab/vtab: the 512 node values u_i, v_i in the interleaved layout of tab_at()
@@ -457,7 +508,7 @@ SUHPE_HD FamilyDesc make_family(float lo, float hi, float c, const float* utab, 
     d.scLS = div_rn(1.0f, sqrt_rn(d.fd));
     d.scSL = div_rn(1.0f, sqrt_rn(d.fs));
     d.scMid = (d.mid == kLL) ? d.scLS * d.scSL : 1.0f;
-    d.cut = cut_index(c, cut_thr);
+    d.cut = cut_index(d.fd, d.fs, c, cut_thr);
     return d;
 }
 

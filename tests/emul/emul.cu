@@ -149,6 +149,29 @@ extern "C" int emul_check_items(const float* S, long n, int cut_bits) {
     return bad;
 }
 
+// per sample: the three families' cut indices, the valid nodes and the node slots the kernel's passes
+// execute (a run is rounded up to whole 64-slot passes) -- for the float64 check of the cut bound and
+// for the executed-work accounting in DESIGN.md
+extern "C" void emul_cut_info(const float* S, long n, int cut_bits, int* cut, int* valid, int* slots_exec) {
+    const Tables& tb = tables();
+    for (long i = 0; i < n; ++i) {
+        FamilyDesc fam[3];
+        fisher_families(S + 3 * i, tb.u, tb.v, cut_bits, fam);
+        int nv = 0, ns = 0;
+        for (int f = 0; f < 3; ++f) {
+            cut[3 * i + f] = fam[f].cut;
+            nv += 512 - fam[f].cut;
+            uint32_t w[3];
+            family_run_words(fam[f], w);
+            for (int r = 0; r < 3; ++r) {
+                const int slots = (int)((w[r] >> 10) & 1023u);
+                ns += (slots + 63) / 64 * 64;
+            }
+        }
+        valid[i] = nv; slots_exec[i] = ns;
+    }
+}
+
 // the run boundaries must reproduce the reference's per-node branch choice exactly:
 // node i is d-small iff fl(fd*u_i) <= 3.75 and s-small iff fl(fs*v_i) <= 3.75
 extern "C" int emul_check_runs(const float* S, long n) {

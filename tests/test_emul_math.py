@@ -93,6 +93,70 @@ def test_negligible_node_cut_is_below_rounding(emul, golden):
     assert_close(cut["logC"], full["logC"], 2e-7, 2e-7, "logC random")
 
 
+def cut_info(emul, S, bits=26):
+    S = np.ascontiguousarray(S, np.float32)
+    n = len(S)
+    cut, valid, slots = np.zeros((n, 3), np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    emul.emul_cut_info(P(S), ctypes.c_long(n), ctypes.c_int(bits), P(cut), P(valid), P(slots))
+    return cut, valid, slots
+
+
+def test_negligible_node_cut_bound_holds_in_float64(emul):
+    """The claim behind the cut (cut_threshold / cut_index in so3_math.cuh): for every family the
+    trapezoid mass of the skipped prefix [0,cut) is below 2^-bits of the normaliser sum F.  Checked
+    with scipy's float64 I0e on the kernel's own fp32 nodes over random spectra from 1e-2 to 1e3
+    (both signs of s3) and a structured sweep through degenerate / sign-flipped / switch-point
+    spectra; also that the cut does something on the benchmark distribution."""
+    from scipy.special import i0e
+    i = np.arange(512, dtype=np.float32)
+    x = i * np.float32(2.0 / 511.0) - np.float32(1)
+    u, v = (np.float32(1) - x).astype(np.float64), (np.float32(1) + x).astype(np.float64)
+    w = np.ones(512)
+    w[0] = w[-1] = 0.5
+
+    def worst_mass(S, bits):
+        S = np.ascontiguousarray(S, np.float32)
+        cut, valid, slots = cut_info(emul, S, bits)
+        S = S.astype(np.float64)
+        fams = [(S[:, 2], S[:, 1], S[:, 0] + S[:, 2]), (S[:, 2], S[:, 0], S[:, 1] + S[:, 2]), (S[:, 1], S[:, 0], S[:, 1] + S[:, 2])]
+        ys = lambda lo, hi, c: i0e(np.abs(0.5 * (hi - lo))[:, None] * u) * i0e(np.abs(0.5 * (hi + lo))[:, None] * v) * np.exp(-c[:, None] * u)
+        F = (ys(*fams[0]) * w).sum(1)
+        worst = 0.0
+        for f, fam in enumerate(fams):
+            cs = np.cumsum(ys(*fam) * w, 1)
+            k = cut[:, f]
+            assert (k >= 0).all() and (k <= 511).all()
+            mass = np.where(k > 0, cs[np.arange(len(S)), np.maximum(k - 1, 0)], 0.0)
+            worst = max(worst, float((mass / F * 2.0 ** bits).max()))
+        return worst, cut, valid, slots
+
+    rng = np.random.default_rng(11)
+    for scale in [0.01, 0.3, 1, 3, 5, 10, 30, 100, 300, 1000]:
+        A = torch.from_numpy(rng.standard_normal((3000, 3, 3)) * scale)
+        U, S, Vh = torch.linalg.svd(A)
+        S[:, 2] *= torch.det(U @ Vh)
+        for bits in (20, 26):
+            worst, *_ = worst_mass(S.numpy(), bits)
+            assert worst <= 1.0, (scale, bits, worst)
+    sweep = [(s1, s1 * r2, s1 * r2 * r3)
+             for s1 in [0, 1e-3, 0.5, 1, 2, 3.75, 5, 7.5, 10, 20, 50, 100, 300, 1000, 1e4]
+             for r2 in [0, 0.01, 0.3, 0.5, 0.9, 0.999, 1]
+             for r3 in [-1, -0.999, -0.9, -0.5, -0.01, 0, 0.01, 0.5, 0.9, 0.999, 1]]
+    worst, *_ = worst_mass(np.array(sweep), 26)
+    assert worst <= 1.0, worst
+    # non-finite spectra: nothing is cut, nothing crashes
+    cut, _, _ = cut_info(emul, np.array([[np.nan, 1, 1], [np.inf, 2, 1], [3e38, 3e38, -3e38]], np.float32))
+    assert (cut == 0).all()
+    # cut off: every node is evaluated
+    assert (cut_info(emul, np.array(sweep), 0)[0] == 0).all()
+    # the benchmark distribution (A = 10 randn): more than a third of the 1536 nodes are provably negligible
+    torch.manual_seed(0)
+    U, S, Vh = torch.linalg.svd(10 * torch.randn(20000, 3, 3))
+    S[:, 2] *= torch.det(U @ Vh)
+    worst, cut, valid, slots = worst_mass(S.numpy(), 26)
+    assert worst <= 1.0 and valid.mean() < 1024
+
+
 def run_laplace(emul, A, R, grid, L):
     A = np.ascontiguousarray(A.reshape(-1, 9), np.float32)
     R = np.ascontiguousarray(R.reshape(-1, 9), np.float32)
