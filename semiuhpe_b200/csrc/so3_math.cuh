@@ -443,14 +443,37 @@ SUHPE_HD int switch_index(float f, const float* t, bool falling) {
 // bound holds for any u*, however it was found); if the check fails the plain e^(-c u) bound
 // (Bd = Bs-term = 1) is used.  tests/test_emul_math.py verifies the claim in float64 over random
 // spectra.  bits <= 0 disables the cut.
+// The search runs in the log2 domain on single-MUFU approximations (relative error ~1e-7 against the
+// 0.03-bit slack added to the threshold); the whole thing costs a thread ~50 instructions per family.
 constexpr float kI0eUp = 0.4690f;
+constexpr float kLog2I0eUp = -1.0923400f;          // log2(0.4690)
 constexpr float kQuadStep = (float)(2.0 / 511.0);
 
-SUHPE_HD float i0e_lower(float a) { return fmaxf(expf(-a), 0.39f / sqrt_rn(fmaxf(a, 1.0f))); }     // I0 >= 1 covers small a
-// ln of min(1, kI0eUp / sqrt(a))
-SUHPE_HD float ln_i0e_upper(float a) { return fminf(0.0f, -0.757153f - 0.5f * logf(fmaxf(a, 1e-30f))); }   // ln 0.4690 = -0.757153
+SUHPE_HD float mufu_lg2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return log2f(x);
+#endif
+}
+SUHPE_HD float mufu_rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
 
-// ln(2^bits / F_lower) plus a little slack for the fp32 evaluation of the bound itself; +inf = no cut
+// I0e(a) >= max(e^-a, 0.39/sqrt(max(a,1)))   (I0 >= 1 covers small a; sqrt(a) I0e(a) >= 0.3989 for a >= 1)
+SUHPE_HD float i0e_lower(float a) { return fmaxf(mufu_ex2(-kLog2e * a), 0.39f * mufu_rsqrt(fmaxf(a, 1.0f))); }
+// log2 of min(1, kI0eUp / sqrt(a)) >= log2 I0e(a)
+SUHPE_HD float lg2_i0e_upper(float a) { return fminf(0.0f, fmaf(-0.5f, mufu_lg2(fmaxf(a, 1e-30f)), kLog2I0eUp)); }
+
+// log2(2^bits / F_lower) plus slack for the approximate evaluation of the bound itself; +inf = no cut
 SUHPE_HD float cut_threshold(const float* s, int bits) {
     if (bits <= 0) return INFINITY;
     const float c0 = s[0] + s[2], fd0 = fabsf(0.5f * (s[1] - s[2])), as0 = fabsf(s[1] + s[2]);
@@ -458,32 +481,36 @@ SUHPE_HD float cut_threshold(const float* s, int bits) {
     if (!(t >= 0.0f) || !(fabsf(s[0]) <= 3.0e38f) || !(as0 <= 3.0e38f) || !(fd0 <= 3.0e38f)) return INFINITY;   // NaN / inf spectra: evaluate everything
     float K = 0.0f, G = 1.0f;
     if (t < 1.0f) {
-        K = fminf(floorf(1.0f / fmaxf(t, 1e-9f)), 510.0f);
+        K = fminf(floorf(mufu_rcp_approx(fmaxf(t, 1e-9f)) * 0.999f), 510.0f);
         // exact geometric sum where 1 - e^-t is well conditioned, else the smallest term times the count
-        G = (t > 1e-3f) ? (1.0f - expf(-t * (K + 1.0f))) / (1.0f - expf(-t)) : (K + 1.0f) * expf(-t * K);
+        const float tl = -kLog2e * t;
+        G = (t > 1e-3f) ? (1.0f - mufu_ex2(tl * (K + 1.0f))) * mufu_rcp_approx(1.0f - mufu_ex2(tl)) : (K + 1.0f) * mufu_ex2(tl * K);
     }
     const float Flow = i0e_lower(as0) * i0e_lower(fd0 * K * kQuadStep) * (G - 0.5f);
-    return 0.69314718f * (float)bits - logf(Flow) + 0.02f;
+    return (float)bits - mufu_lg2(Flow) + 0.03f;
 }
 
-// ln of the prefix bound without its e^(-c u) / (1 - e^(-c h)) part: ln(Bd (Bs + e^(-c v0))), capped at 0
-SUHPE_HD float cut_prefix_factor(float fd, float fs, float c, float u) {
+// log2 of the prefix bound without its e^(-c u) / (1 - e^(-c h)) part: log2(Bd (Bs + e^(-c v0))), capped at 0
+SUHPE_HD float cut_prefix_factor(float fd, float fs, float cl, float u) {
     const float v0 = 0.5f * fmaxf(2.0f - u, 0.0f);
-    const float bs = expf(ln_i0e_upper(fs * v0)) + expf(-c * v0);
-    return ln_i0e_upper(fd * u) + fminf(0.0f, logf(bs));
+    const float bs = fminf(1.0f, kI0eUp * mufu_rsqrt(fmaxf(fs * v0, 1e-30f))) + mufu_ex2(-cl * v0);
+    return lg2_i0e_upper(fd * u) + fminf(0.0f, mufu_lg2(bs));
 }
 
-SUHPE_HD int cut_index(float fd, float fs, float c, float thr) {
-    if (!(c > 0.0f) || !(thr < INFINITY)) return 0;
-    const float geo = -logf(1.0f - expf(-c * kQuadStep));          // c h -> 0: +inf -> no cut
-    const float rhs = thr + geo;
+// cl = c log2(e)
+SUHPE_HD int cut_index(float fd, float fs, float cl, float thr) {
+    if (!(cl > 0.0f) || !(thr < INFINITY)) return 0;
+    const float rhs = thr - mufu_lg2(1.0f - mufu_ex2(-cl * kQuadStep));          // c h -> 0: +inf -> no cut
     if (!(rhs < INFINITY)) return 0;
-    const float ic = div_rn(1.0f, c);
-    float u = 2.0f;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) u = fminf(fmaxf((rhs + cut_prefix_factor(fd, fs, c, u)) * ic, 0.0f), 4.0f);
-    u += 2.0f * kQuadStep;                                           // safety margin before the check
-    if (!(fmaf(c, u, -cut_prefix_factor(fd, fs, c, u)) >= rhs)) u = rhs * ic;    // fall back to the plain bound
+    const float ic = mufu_rcp_approx(cl);
+    float u = rhs * ic;                                               // plain bound: always valid
+    if (u < 2.0f) {
+        float w = u;
+#pragma unroll 1
+        for (int it = 0; it < 3; ++it) w = fmaxf((rhs + cut_prefix_factor(fd, fs, cl, w)) * ic, 0.0f);
+        w += 2.0f * kQuadStep;                                        // safety margin before the check
+        if (fmaf(cl, w, -cut_prefix_factor(fd, fs, cl, w)) >= rhs) u = w;
+    }
     // nodes with u_i >= u:  i <= (2 - u) * 255.5 ; one more node of slack
     const float lim = (2.0f - u) * 255.5f - 1.0f;
     return (int)fminf(fmaxf(floorf(lim), 0.0f), (float)(kQuadNodes - 1));   // NaN -> 0
@@ -508,7 +535,7 @@ SUHPE_HD FamilyDesc make_family(float lo, float hi, float c, const float* utab, 
     d.scLS = div_rn(1.0f, sqrt_rn(d.fd));
     d.scSL = div_rn(1.0f, sqrt_rn(d.fs));
     d.scMid = (d.mid == kLL) ? d.scLS * d.scSL : 1.0f;
-    d.cut = cut_index(d.fd, d.fs, c, cut_thr);
+    d.cut = cut_index(d.fd, d.fs, cl, cut_thr);
     return d;
 }
 
