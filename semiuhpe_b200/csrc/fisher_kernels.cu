@@ -49,13 +49,14 @@ struct __align__(16) WarpScratch {
 // lane's LDS.128 lands directly in two f32x2 register pairs.  A run body needs at most two
 // such loads per 64 nodes:
 //   LL  a = (iu, iv)  b = (u, Lu+Lv)        LS  a = (iu, v)  b = (u, Lu)
-//   SL  a = (iv, Lv)  b = (u)               SS  a = (u, v)
+//   SL  a = (iv, Lv)  b = LS's b (u, -)      SS  a = (u, v)
+// Every column has the same 16-byte stride, so a run walks ONE address register and reaches its
+// two columns through immediate offsets.
 // 288 entries: a run's last pass may read up to 31 pairs past node 511 (discarded).
 constexpr int kTabPairs = 288;
 struct __align__(16) QuadTables {
     float4 LLa[kTabPairs], LLb[kTabPairs], LSa[kTabPairs], LSb[kTabPairs];
     float4 SLa[kTabPairs], SSa[kTabPairs];
-    float2 SLb[kTabPairs];
     NodeVals first, last;                     // nodes 0 and 511 (trapezoid half weights)
 };
 
@@ -126,9 +127,10 @@ __device__ __forceinline__ float4 lds128(unsigned a) {
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ float2 lds64(unsigned a) {
-    float2 v;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+template <unsigned OFF>
+__device__ __forceinline__ float4 lds128_at(unsigned a) {       // [a + OFF], OFF folded into the instruction
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
     return v;
 }
 // ordered after the phase-1 stores of the same warp (compiler barrier)
@@ -143,17 +145,19 @@ __device__ __forceinline__ float4 lds128_ordered(unsigned a) {
 // lane.  Slots outside the run -- the odd head slot and the tail of the run's last pass -- are
 // zeroed by a select on the ALU pipe, so the FMA pipe sees one straight-line FFMA2 body per
 // type.
-//   ta / tbb : shared addresses of this lane's first pair in the type's two table columns
-//   base     : 2*lane - head (wraps for the head slot), lenm = nvalid - head
+//   ta   : shared address of this lane's first pair, relative to the start of QuadTables
+//   base : 2*lane - head (wraps for the head slot), lenm = nvalid - head
 template <int T, int W>
-__device__ __forceinline__ void quad_pass(unsigned ta, unsigned tbb, unsigned base, unsigned lenm, const RunConsts& k,
+__device__ __forceinline__ void quad_pass(unsigned ta, unsigned base, unsigned lenm, const RunConsts& k,
                                           f2& accY, f2& accUY) {
+    constexpr unsigned offA = (T == kLL) ? offsetof(QuadTables, LLa) : (T == kLS) ? offsetof(QuadTables, LSa)
+                            : (T == kSL) ? offsetof(QuadTables, SLa) : offsetof(QuadTables, SSa);
+    constexpr unsigned offB = (T == kLL) ? offsetof(QuadTables, LLb) : offsetof(QuadTables, LSb);
     float4 a[W], b[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-        a[w] = lds128(ta + 512 * w);
-        if (T == kLL || T == kLS) b[w] = lds128(tbb + 512 * w);
-        if (T == kSL) { const float2 h = lds64(tbb + 256 * w); b[w].x = h.x; b[w].y = h.y; }
+        a[w] = (w == 0) ? lds128_at<offA>(ta) : lds128_at<offA + 512>(ta);
+        if (T != kSS) b[w] = (w == 0) ? lds128_at<offB>(ta) : lds128_at<offB + 512>(ta);
     }
     f2 pd[W], ps[W], e[W], u[W];
 #pragma unroll
@@ -201,25 +205,22 @@ __device__ __forceinline__ void quad_pass(unsigned ta, unsigned tbb, unsigned ba
 
 // One run of uniform type T described by a run word (see run_word in so3_math.cuh); adds the
 // run's lane-partial sums of y and u*y, times the run's constant factor, to Y / UY.
-// tab: shared address of the QuadTables block + 16*lane (tab2: + 8*lane, the float2 column).
+// tab: shared address of the QuadTables block + 16*lane; lane2 = 2*lane.
 template <int T>
-__device__ __forceinline__ void quad_run(unsigned tab, unsigned tab2, unsigned lane2, uint32_t word, float scale,
+__device__ __forceinline__ void quad_run(unsigned tab, int lane2, uint32_t word, float scale,
                                          const RunConsts& k, float& Y, float& UY) {
-    constexpr unsigned offA = (T == kLL) ? offsetof(QuadTables, LLa) : (T == kLS) ? offsetof(QuadTables, LSa)
-                            : (T == kSL) ? offsetof(QuadTables, SLa) : offsetof(QuadTables, SSa);
-    constexpr unsigned offB = (T == kLL) ? offsetof(QuadTables, LLb) : (T == kLS) ? offsetof(QuadTables, LSb)
-                            : offsetof(QuadTables, SLb);
-    const unsigned m0 = word & 511u, head = (word >> 9) & 1u;
-    int slots = (int)((word >> 10) & 1023u);
-    unsigned ta = tab + offA + 16u * m0;
-    unsigned tbb = (T == kSL) ? tab2 + offB + 8u * m0 : tab + offB + 16u * m0;
-    unsigned base = lane2 - head;                    // slot of the lo half relative to the run start (wraps for the head slot)
-    const unsigned lenm = (unsigned)slots - head;
+    const int head = (int)(word & 1u);
+    const int slots = (int)(word >> 16);
+    unsigned ta = tab + (word & 0x1ff0u);
+    int base = lane2 - head;                         // slot of the lo half relative to the run start (-1 = the masked head slot)
+    const unsigned lenm = (unsigned)(slots - head);
+    // passes of 128 slots while more than 64 remain: slots - (base - base0) > 64  <=>  base < slots - 64 + base0
+    const int lim = slots - 64 + base;
     f2 accY = pk(0.f, 0.f), accUY = pk(0.f, 0.f);
 #pragma unroll 1
-    for (; slots > 64; slots -= 128, ta += 1024, tbb += (T == kSL) ? 512 : 1024, base += 128)
-        quad_pass<T, 2>(ta, tbb, base, lenm, k, accY, accUY);
-    if (slots > 0) quad_pass<T, 1>(ta, tbb, base, lenm, k, accY, accUY);
+    for (; base < lim; base += 128, ta += 1024)
+        quad_pass<T, 2>(ta, (unsigned)base, lenm, k, accY, accUY);
+    if (base < lim + 64) quad_pass<T, 1>(ta, (unsigned)base, lenm, k, accY, accUY);
     float lo, hi;
     upk(accY, lo, hi); Y = fmaf(scale, lo + hi, Y);
     upk(accUY, lo, hi); UY = fmaf(scale, lo + hi, UY);
@@ -261,7 +262,6 @@ fisher_fused_kernel(FisherArgs p) {
         q = reinterpret_cast<float*>(&tb.LSa[m]); q[h] = n.iu; q[2 + h] = n.v;
         q = reinterpret_cast<float*>(&tb.LSb[m]); q[h] = n.u;  q[2 + h] = n.Lu;
         q = reinterpret_cast<float*>(&tb.SLa[m]); q[h] = n.iv; q[2 + h] = n.Lv;
-        q = reinterpret_cast<float*>(&tb.SLb[m]); q[h] = n.u;
         q = reinterpret_cast<float*>(&tb.SSa[m]); q[h] = n.u;  q[2 + h] = n.v;
         if (i == 0) tb.first = n;
         if (i == kQuadNodes - 1) tb.last = n;
@@ -271,9 +271,8 @@ fisher_fused_kernel(FisherArgs p) {
     // shared-window addresses, laundered through asm so the hot loop keeps them in registers
     // instead of re-deriving the window base (S2UR SR_CgaCtaId) at every use
     unsigned tab_s = (unsigned)__cvta_generic_to_shared(&tb) + 16u * lane;          // float4 columns, this lane's pair
-    unsigned tab2_s = (unsigned)__cvta_generic_to_shared(&tb) + 8u * lane;          // float2 column
     unsigned desc_s = (unsigned)__cvta_generic_to_shared(ws.desc);
-    asm volatile("" : "+r"(tab_s), "+r"(tab2_s), "+r"(desc_s));
+    asm volatile("" : "+r"(tab_s), "+r"(desc_s));
     // Schedule: `full_rounds` rounds in which every warp of the grid takes one 32-sample tile, then ONE
     // closing round that spreads the remaining samples evenly over all warps (samples_per_warp < 32
     // each), so every warp finishes together whatever n is (a plain round-robin of 32-sample tiles
@@ -345,7 +344,7 @@ fisher_fused_kernel(FisherArgs p) {
 
         // ---- phase 2: quadrature (warp per sample) ---------------------------
         float Y0 = 1.f, UY0 = 0.f, N1 = 0.f, N2 = 0.f;
-        const unsigned lane2 = 2u * lane;
+        const int lane2 = 2 * lane;
 #pragma unroll 1
         for (int j = 0; j < count; ++j) {
             float pY0 = 0.f, pUY0 = 0.f, pN1 = 0.f, pN2 = 0.f;
@@ -360,12 +359,12 @@ fisher_fused_kernel(FisherArgs p) {
                 k.k2 = -(d0.y * kLog2e);
                 const uint32_t w0 = __float_as_uint(d2.y), w1 = __float_as_uint(d2.z), w2 = __float_as_uint(d2.w);
                 float Y = 0.f, UY = 0.f;
-                if (w0 & (1023u << 10)) quad_run<kLS>(tab_s, tab2_s, lane2, w0, d1.z, k, Y, UY);
-                if (w1 & (1023u << 10)) {
-                    if (w1 & (1u << 20)) quad_run<kLL>(tab_s, tab2_s, lane2, w1, d2.x, k, Y, UY);
-                    else                 quad_run<kSS>(tab_s, tab2_s, lane2, w1, d2.x, k, Y, UY);
+                if (w0 >> 16) quad_run<kLS>(tab_s, lane2, w0, d1.z, k, Y, UY);
+                if (w1 >> 16) {
+                    if (w1 & 2u) quad_run<kLL>(tab_s, lane2, w1, d2.x, k, Y, UY);
+                    else         quad_run<kSS>(tab_s, lane2, w1, d2.x, k, Y, UY);
                 }
-                if (w2 & (1023u << 10)) quad_run<kSL>(tab_s, tab2_s, lane2, w2, d1.w, k, Y, UY);
+                if (w2 >> 16) quad_run<kSL>(tab_s, lane2, w2, d1.w, k, Y, UY);
                 if (f == 0) { pY0 = Y; pUY0 = UY; }
                 else if (f == 1) pN1 = Y - UY;
                 else pN2 = Y - UY;
@@ -596,7 +595,6 @@ __device__ __forceinline__ void probe_pass(unsigned ta, unsigned tbb, unsigned b
         else {
             a[w] = lds128(ta + 512 * w);
             if (T == kLL || T == kLS) b[w] = lds128(tbb + 512 * w);
-            if (T == kSL) { const float2 h = lds64(tbb + 256 * w); b[w].x = h.x; b[w].y = h.y; }
         }
     }
     f2 pd[W], ps[W], e[W], u[W];

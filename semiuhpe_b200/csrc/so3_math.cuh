@@ -548,19 +548,25 @@ SUHPE_HD void fisher_families(const float* s, const float* utab, const float* vt
 
 // ----------------------------------------------------------------------------
 // Run words.  The thread that owns a sample packs each of the (up to) three runs of a family
-// into one word, so the warp that replays the quadrature does no boundary arithmetic:
-//   bits 0-8  m0: first node pair of the run (start >> 1)
-//   bit  9    head: the run starts at the odd node of that pair (slot 0 of the first pass is masked)
-//   bits 10-19 slots: end - 2*m0, the number of node slots from the pair's first node to the run's
-//             end (0 = empty run); passes of 128 slots while more than 64 remain, then one of 64
-//   bit  20   the middle run is LL (else SS)
+// into one word, laid out so that the warp that replays the quadrature decodes it with one mask and
+// one shift:
+//   bit  0     head: the run starts at the odd node of its first pair (slot 0 of the first pass is masked)
+//   bit  1     the middle run is LL (else SS)
+//   bits 4-12  16*m0: byte offset of the run's first node pair (start >> 1) in a float4 table column
+//   bits 16-25 slots: end - 2*m0, the number of node slots from the pair's first node to the run's
+//              end (0 = empty run); passes of 128 slots while more than 64 remain, then one of 64
 // ----------------------------------------------------------------------------
 SUHPE_HD uint32_t run_word(int lo, int end, int cut, bool mid_ll) {
     const int start = lo > cut ? lo : cut;
-    if (end <= start) return mid_ll ? (1u << 20) : 0u;
+    const uint32_t flag = mid_ll ? 2u : 0u;
+    if (end <= start) return flag;
     const int m0 = start >> 1;
-    return (uint32_t)m0 | ((uint32_t)(start & 1) << 9) | ((uint32_t)(end - 2 * m0) << 10) | (mid_ll ? (1u << 20) : 0u);
+    return (uint32_t)(start & 1) | flag | ((uint32_t)m0 << 4) | ((uint32_t)(end - 2 * m0) << 16);
 }
+SUHPE_HD unsigned run_word_head(uint32_t w) { return w & 1u; }
+SUHPE_HD bool run_word_mid_ll(uint32_t w) { return (w & 2u) != 0; }
+SUHPE_HD unsigned run_word_m0(uint32_t w) { return (w >> 4) & 511u; }
+SUHPE_HD int run_word_slots(uint32_t w) { return (int)(w >> 16); }
 SUHPE_HD void family_run_words(const FamilyDesc& d, uint32_t* w) {
     w[0] = run_word(0, d.b0, d.cut, false);
     w[1] = run_word(d.b0, d.b1, d.cut, d.mid == kLL);

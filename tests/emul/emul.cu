@@ -49,8 +49,8 @@ static const Tables& tables() { static Tables t; return t; }
 // 64 remain, then one of 64; slot masks from (base, lenm); the run's factor applied at the end
 static void run_lane(const FamilyDesc& d, int type, uint32_t word, int lane, float* Y, float* UY) {
     const Tables& tb = tables();
-    const unsigned m0 = word & 511u, head = (word >> 9) & 1u;
-    int slots = (int)((word >> 10) & 1023u);
+    const unsigned m0 = run_word_m0(word), head = run_word_head(word);
+    int slots = run_word_slots(word);
     if (slots == 0) return;
     const unsigned lenm = (unsigned)slots - head;
     unsigned base = 2u * lane - head, m = m0;
@@ -89,7 +89,7 @@ static void quadrature(const float* s, int cut_bits, float* F, float* N0, float*
             family_run_words(d, w);
             float Y = 0, UY = 0;
             run_lane(d, kLS, w[0], lane, &Y, &UY);
-            run_lane(d, (w[1] >> 20) & 1 ? kLL : kSS, w[1], lane, &Y, &UY);
+            run_lane(d, run_word_mid_ll(w[1]) ? kLL : kSS, w[1], lane, &Y, &UY);
             run_lane(d, kSL, w[2], lane, &Y, &UY);
             if (f == 0) { pY0[lane] = Y; pUY0[lane] = UY; }
             else if (f == 1) pN1[lane] = Y - UY;
@@ -124,9 +124,9 @@ extern "C" int emul_check_items(const float* S, long n, int cut_bits) {
             family_run_words(fam[f], w);
             int seen[512] = {};
             for (int r = 0; r < 3; ++r) {
-                const int type = r == 0 ? kLS : (r == 2 ? kSL : ((w[r] >> 20) & 1 ? kLL : kSS));
-                const unsigned m0 = w[r] & 511u, head = (w[r] >> 9) & 1u;
-                int slots = (int)((w[r] >> 10) & 1023u);
+                const int type = r == 0 ? kLS : (r == 2 ? kSL : (run_word_mid_ll(w[r]) ? kLL : kSS));
+                const unsigned m0 = run_word_m0(w[r]), head = run_word_head(w[r]);
+                int slots = run_word_slots(w[r]);
                 if (slots == 0) continue;
                 unsigned m = m0;
                 int done = 0;
@@ -164,7 +164,7 @@ extern "C" void emul_cut_info(const float* S, long n, int cut_bits, int* cut, in
             uint32_t w[3];
             family_run_words(fam[f], w);
             for (int r = 0; r < 3; ++r) {
-                const int slots = (int)((w[r] >> 10) & 1023u);
+                const int slots = run_word_slots(w[r]);
                 ns += (slots + 63) / 64 * 64;
             }
         }
