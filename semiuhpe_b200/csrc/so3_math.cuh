@@ -430,14 +430,15 @@ SUHPE_HD int switch_index(float f, const float* t, bool falling) {
 //       y0(u_k) >= I0e(s2+s3) I0e(fd0 K h) e^(-c0 h k)
 //   and with the trapezoid's half weight at k = 0
 //       F >= I0e_lo(s2+s3) I0e_lo(fd0 K h) (G_K - 1/2),  G_K = sum_{k<=K} e^(-c0 h k),
-//   I0e_lo(a) = max(e^-a, 0.39 / sqrt(max(a,1))) <= I0e(a);  K = floor(1/(c0 h)) (one e-folding), capped at 510.
+//   I0e_lo(a) = max(e^-a, 0.39 / sqrt(max(a,1))) <= I0e(a);  K = floor(1/(c0 h)) (one e-folding), capped at 510;
+//   a second group K < k <= K2 = 3K+2 adds I0e_lo(s2+s3) I0e_lo(fd0 K2 h) (G_K2 - G_K) the same way.
 //
 //   upper bound of a prefix {i : u_i >= u*} of a family (fd, fs, c):  with I0e(a) <= min(1, kI0eUp/sqrt(a))
 //   (sup_a sqrt(a) I0e(a) = 0.4688), the d factor is <= Bd = I0e_up(fd u*) on the whole prefix; the s
-//   factor is <= 1 where v < v0 and <= Bs = I0e_up(fs v0) where v >= v0, for any split v0 -- taken at
-//   half the prefix, v0 = (2-u*)/2; and sum e^(-c u_i) over nodes with u_i >= w is a geometric series
+//   factor is <= 1 where v < v0 and <= Bs = I0e_up(fs v0) where v >= v0, for any split v0 of the
+//   prefix's v range [0, v* = 2-u*]; and sum e^(-c u_i) over nodes with u_i >= w is a geometric series
 //   <= e^(-c w) / (1 - e^(-c h)).  Hence
-//       mass(prefix) <= Bd (Bs + e^(-c v0)) e^(-c u*) / (1 - e^(-c h)).
+//       mass(prefix) <= Bd (Bs + e^(-c (v*-v0))) e^(-c u*) / (1 - e^(-c h)).
 //
 // A candidate u* is found by a few fixed-point steps and then CHECKED against the inequality (the
 // bound holds for any u*, however it was found); if the check fails the plain e^(-c u) bound
@@ -479,21 +480,34 @@ SUHPE_HD float cut_threshold(const float* s, int bits) {
     const float c0 = s[0] + s[2], fd0 = fabsf(0.5f * (s[1] - s[2])), as0 = fabsf(s[1] + s[2]);
     const float t = c0 * kQuadStep;
     if (!(t >= 0.0f) || !(fabsf(s[0]) <= 3.0e38f) || !(as0 <= 3.0e38f) || !(fd0 <= 3.0e38f)) return INFINITY;   // NaN / inf spectra: evaluate everything
-    float K = 0.0f, G = 1.0f;
+    // two node groups next to x = 1: k <= K (one e-folding) and K < k <= K2 (two more)
+    float sum = 0.5f;                                                  // t >= 1: the half-weighted end node alone
     if (t < 1.0f) {
-        K = fminf(floorf(mufu_rcp_approx(fmaxf(t, 1e-9f)) * 0.999f), 510.0f);
-        // exact geometric sum where 1 - e^-t is well conditioned, else the smallest term times the count
+        const float K = fminf(floorf(mufu_rcp_approx(fmaxf(t, 1e-9f)) * 0.999f), 510.0f);
+        const float K2 = fminf(3.0f * K + 2.0f, 510.0f);
         const float tl = -kLog2e * t;
-        G = (t > 1e-3f) ? (1.0f - mufu_ex2(tl * (K + 1.0f))) * mufu_rcp_approx(1.0f - mufu_ex2(tl)) : (K + 1.0f) * mufu_ex2(tl * K);
+        float G1, G2;                                                  // sum_{k<=K} e^(-t k),  sum_{K<k<=K2} e^(-t k)
+        if (t > 1e-3f) {                                               // 1 - e^-t well conditioned: exact geometric sums
+            const float q = mufu_rcp_approx(1.0f - mufu_ex2(tl)), eK = mufu_ex2(tl * (K + 1.0f));
+            G1 = (1.0f - eK) * q;
+            G2 = eK * (1.0f - mufu_ex2(tl * (K2 - K))) * q;
+        } else {                                                       // else the smallest term times the count
+            G1 = (K + 1.0f) * mufu_ex2(tl * K);
+            G2 = (K2 - K) * mufu_ex2(tl * K2);
+        }
+        sum = i0e_lower(fd0 * K * kQuadStep) * (G1 - 0.5f) + i0e_lower(fd0 * K2 * kQuadStep) * G2;
     }
-    const float Flow = i0e_lower(as0) * i0e_lower(fd0 * K * kQuadStep) * (G - 0.5f);
+    const float Flow = i0e_lower(as0) * sum;
     return (float)bits - mufu_lg2(Flow) + 0.03f;
 }
 
 // log2 of the prefix bound without its e^(-c u) / (1 - e^(-c h)) part: log2(Bd (Bs + e^(-c v0))), capped at 0
-SUHPE_HD float cut_prefix_factor(float fd, float fs, float cl, float u) {
-    const float v0 = 0.5f * fmaxf(2.0f - u, 0.0f);
-    const float bs = fminf(1.0f, kI0eUp * mufu_rsqrt(fmaxf(fs * v0, 1e-30f))) + mufu_ex2(-cl * v0);
+SUHPE_HD float cut_prefix_factor(float fd, float fs, float cl, float icl, float u) {
+    // split of the s factor: v0 = the later of half the prefix and four e-foldings (5.77 octaves of the
+    // log2-domain slope cl) before its end -- the prefix mass sits at its end
+    const float v = fmaxf(2.0f - u, 0.0f);
+    const float v0 = fmaxf(0.5f * v, v - 5.77f * icl);
+    const float bs = fminf(1.0f, kI0eUp * mufu_rsqrt(fmaxf(fs * v0, 1e-30f))) + mufu_ex2(-cl * (v - v0));
     return lg2_i0e_upper(fd * u) + fminf(0.0f, mufu_lg2(bs));
 }
 
@@ -507,9 +521,9 @@ SUHPE_HD int cut_index(float fd, float fs, float cl, float thr) {
     if (u < 2.0f) {
         float w = u;
 #pragma unroll 1
-        for (int it = 0; it < 3; ++it) w = fmaxf((rhs + cut_prefix_factor(fd, fs, cl, w)) * ic, 0.0f);
-        w += 2.0f * kQuadStep;                                        // safety margin before the check
-        if (fmaf(cl, w, -cut_prefix_factor(fd, fs, cl, w)) >= rhs) u = w;
+        for (int it = 0; it < 3; ++it) w = fmaxf((rhs + cut_prefix_factor(fd, fs, cl, ic, w)) * ic, 0.0f);
+        w += 0.5f * kQuadStep;                                        // safety margin before the check
+        if (fmaf(cl, w, -cut_prefix_factor(fd, fs, cl, ic, w)) >= rhs) u = w;
     }
     // nodes with u_i >= u:  i <= (2 - u) * 255.5 ; one more node of slack
     const float lim = (2.0f - u) * 255.5f - 1.0f;
