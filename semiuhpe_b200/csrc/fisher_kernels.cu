@@ -117,9 +117,23 @@ __device__ __forceinline__ f2 small2(f2 a) {
 
 struct RunConsts { float fd, fs, ifd, ifs, k1L, k1S, k2; };
 
-// accumulate in place (keeps the accumulators pinned to one register pair)
+// unconditional in-place accumulation (body probe)
 __device__ __forceinline__ void acc_add2(f2& acc, f2 y) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(y)); }
 __device__ __forceinline__ void acc_fma2(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
+// Accumulate one node pair if it lies inside the run: `left` = pairs from this lane's first pair of
+// the pass to the run's end, the pair of half w counts iff left > 32*w.  One predicate per pair; the
+// select (ALU pipe) also keeps whatever the masked lanes computed from table entries past the run
+// (inf / NaN included) away from the accumulators.
+template <int LIM>
+__device__ __forceinline__ void acc_pair(f2& accY, f2& accUY, f2 y, f2 u, int left) {
+    float ylo, yhi;
+    upk(y, ylo, yhi);
+    const bool in = left > LIM;
+    const f2 ym = pk(in ? ylo : 0.0f, in ? yhi : 0.0f);
+    acc_add2(accY, ym);
+    acc_fma2(accUY, u, ym);
+}
 
 // shared-memory loads by 32-bit shared-window address (no generic->shared conversion in the hot loop)
 __device__ __forceinline__ float4 lds128(unsigned a) {
@@ -140,16 +154,15 @@ __device__ __forceinline__ float4 lds128_ordered(unsigned a) {
     return v;
 }
 
-// One pass: W*64 node slots of a run of type T; lane l takes the adjacent node pairs at
+// One pass: W*32 node pairs of a run of type T; lane l takes the adjacent node pairs at
 // ta, ta+512 B (nodes 2m, 2m+1).  W = 2 keeps four independent Horner chains in flight per
-// lane.  Slots outside the run -- the odd head slot and the tail of the run's last pass -- are
-// zeroed by a select on the ALU pipe, so the FMA pipe sees one straight-line FFMA2 body per
-// type.
+// lane.  Runs are pair-aligned (family_plan), so inside a run every pair is fully valid; pairs past
+// the run's end -- the tail of its last pass -- are dropped by the predicate of acc_pair.  The FMA
+// pipe sees one straight-line FFMA2 body per type.
 //   ta   : shared address of this lane's first pair, relative to the start of QuadTables
-//   base : 2*lane - head (wraps for the head slot), lenm = nvalid - head
+//   left : pairs from this lane's first pair of the pass to the run's end (<= 0: outside)
 template <int T, int W>
-__device__ __forceinline__ void quad_pass(unsigned ta, unsigned base, unsigned lenm, const RunConsts& k,
-                                          f2& accY, f2& accUY) {
+__device__ __forceinline__ void quad_pass(unsigned ta, int left, const RunConsts& k, f2& accY, f2& accUY) {
     constexpr unsigned offA = (T == kLL) ? offsetof(QuadTables, LLa) : (T == kLS) ? offsetof(QuadTables, LSa)
                             : (T == kSL) ? offsetof(QuadTables, SLa) : offsetof(QuadTables, SSa);
     constexpr unsigned offB = (T == kLL) ? offsetof(QuadTables, LLb) : offsetof(QuadTables, LSb);
@@ -193,34 +206,26 @@ __device__ __forceinline__ void quad_pass(unsigned ta, unsigned base, unsigned l
     }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-        float ylo, yhi;
-        upk(mul2(mul2(pd[w], ps[w]), ex22(e[w])), ylo, yhi);
-        ylo = (base + 64u * w < lenm) ? ylo : 0.0f;
-        yhi = (base + 64u * w + 1u < lenm) ? yhi : 0.0f;
-        const f2 y = pk(ylo, yhi);
-        acc_add2(accY, y);
-        acc_fma2(accUY, u[w], y);
+        const f2 y = mul2(mul2(pd[w], ps[w]), ex22(e[w]));
+        if (w == 0) acc_pair<0>(accY, accUY, y, u[w], left);
+        else        acc_pair<32>(accY, accUY, y, u[w], left);
     }
 }
 
-// One run of uniform type T described by a run word (see run_word in so3_math.cuh); adds the
+// One run of uniform type T described by a run word (see family_plan in so3_math.cuh); adds the
 // run's lane-partial sums of y and u*y, times the run's constant factor, to Y / UY.
-// tab: shared address of the QuadTables block + 16*lane; lane2 = 2*lane.
+// tab: shared address of the QuadTables block + 16*lane; lim32 = 32 - lane.
 template <int T>
-__device__ __forceinline__ void quad_run(unsigned tab, int lane2, uint32_t word, float scale,
+__device__ __forceinline__ void quad_run(unsigned tab, int lane, int lim32, uint32_t word, float scale,
                                          const RunConsts& k, float& Y, float& UY) {
-    const int head = (int)(word & 1u);
-    const int slots = (int)(word >> 16);
     unsigned ta = tab + (word & 0x1ff0u);
-    int base = lane2 - head;                         // slot of the lo half relative to the run start (-1 = the masked head slot)
-    const unsigned lenm = (unsigned)(slots - head);
-    // passes of 128 slots while more than 64 remain: slots - (base - base0) > 64  <=>  base < slots - 64 + base0
-    const int lim = slots - 64 + base;
+    int left = (int)(word >> 16) - lane;             // pairs from this lane's pair to the run's end
     f2 accY = pk(0.f, 0.f), accUY = pk(0.f, 0.f);
+    // passes of 64 pairs while more than 32 remain: pairs_left = left + lane > 32  <=>  left > 32 - lane
 #pragma unroll 1
-    for (; base < lim; base += 128, ta += 1024)
-        quad_pass<T, 2>(ta, (unsigned)base, lenm, k, accY, accUY);
-    if (base < lim + 64) quad_pass<T, 1>(ta, (unsigned)base, lenm, k, accY, accUY);
+    for (; left > lim32; left -= 64, ta += 1024)
+        quad_pass<T, 2>(ta, left, k, accY, accUY);
+    if (left > lim32 - 32) quad_pass<T, 1>(ta, left, k, accY, accUY);
     float lo, hi;
     upk(accY, lo, hi); Y = fmaf(scale, lo + hi, Y);
     upk(accUY, lo, hi); UY = fmaf(scale, lo + hi, UY);
@@ -230,6 +235,18 @@ __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(kFull, x, off);
     return x;
+}
+
+// node i's constants read back from the pair-interleaved table columns (edge nodes, phase 1)
+__device__ __forceinline__ NodeVals table_node(const QuadTables& tb, int i) {
+    const int m = i >> 1, h = i & 1;
+    NodeVals n;
+    const float* q;
+    q = reinterpret_cast<const float*>(&tb.SSa[m]); n.u = q[h];  n.v = q[2 + h];
+    q = reinterpret_cast<const float*>(&tb.LLa[m]); n.iu = q[h]; n.iv = q[2 + h];
+    q = reinterpret_cast<const float*>(&tb.LSb[m]); n.Lu = q[2 + h];
+    q = reinterpret_cast<const float*>(&tb.SLa[m]); n.Lv = q[2 + h];
+    return n;
 }
 
 // trapezoid half weight of an end node, with the constant factor of the run it sits in
@@ -321,30 +338,42 @@ fisher_fused_kernel(FisherArgs p) {
         {
             FamilyDesc fam[3];
             fisher_families(s, reinterpret_cast<const float*>(tb.SSa), reinterpret_cast<const float*>(tb.SSa) + 2, p.cut_bits, fam);
+            float eY[3], eUY[3];                 // this thread's edge nodes (pairs that straddle a type boundary)
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
                 const FamilyDesc& d = fam[f];
-                uint32_t rw[3];
-                family_run_words(d, rw);
+                FamilyPlan pl;
+                family_plan(d, pl);
                 ws.desc[(f * 3 + 0) * 32 + lane] = make_float4(d.fd, d.fs, d.ifd, d.ifs);
                 ws.desc[(f * 3 + 1) * 32 + lane] = make_float4(d.k1L, d.k1S, d.scLS, d.scSL);
-                ws.desc[(f * 3 + 2) * 32 + lane] = make_float4(d.scMid, __uint_as_float(rw[0]), __uint_as_float(rw[1]), __uint_as_float(rw[2]));
+                ws.desc[(f * 3 + 2) * 32 + lane] = make_float4(d.scMid, __uint_as_float(pl.word[0]), __uint_as_float(pl.word[1]), __uint_as_float(pl.word[2]));
+                eY[f] = 0.f; eUY[f] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (pl.edge[k] >= 0) {
+                        const NodeVals nv = table_node(tb, pl.edge[k]);
+                        const int t = edge_type(d, k);
+                        const float y = node_typed(d, t, nv) * type_scale(d, t);
+                        eY[f] += y;
+                        eUY[f] = fmaf(nv.u, y, eUY[f]);
+                    }
+                }
             }
             const float uf = tb.first.u, ul = tb.last.u;
             // (node 0 is only corrected where it was evaluated: a family with cut > 0 skipped it)
             const float f0 = fam[0].cut ? 0.f : end_node(fam[0], 0, tb.first), l0 = end_node(fam[0], kQuadNodes - 1, tb.last);
             const float f1 = fam[1].cut ? 0.f : end_node(fam[1], 0, tb.first), l1 = end_node(fam[1], kQuadNodes - 1, tb.last);
             const float f2v = fam[2].cut ? 0.f : end_node(fam[2], 0, tb.first), l2 = end_node(fam[2], kQuadNodes - 1, tb.last);
-            cY0 = 0.5f * (f0 + l0);
-            cUY0 = 0.5f * fmaf(uf, f0, ul * l0);
-            cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1));
-            cN2 = 0.5f * ((f2v + l2) - fmaf(uf, f2v, ul * l2));
+            cY0 = 0.5f * (f0 + l0) - eY[0];
+            cUY0 = 0.5f * fmaf(uf, f0, ul * l0) - eUY[0];
+            cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1)) - (eY[1] - eUY[1]);
+            cN2 = 0.5f * ((f2v + l2) - fmaf(uf, f2v, ul * l2)) - (eY[2] - eUY[2]);
         }
         __syncwarp();
 
         // ---- phase 2: quadrature (warp per sample) ---------------------------
         float Y0 = 1.f, UY0 = 0.f, N1 = 0.f, N2 = 0.f;
-        const int lane2 = 2 * lane;
+        const int lim32 = 32 - lane;
 #pragma unroll 1
         for (int j = 0; j < count; ++j) {
             float pY0 = 0.f, pUY0 = 0.f, pN1 = 0.f, pN2 = 0.f;
@@ -359,12 +388,12 @@ fisher_fused_kernel(FisherArgs p) {
                 k.k2 = -(d0.y * kLog2e);
                 const uint32_t w0 = __float_as_uint(d2.y), w1 = __float_as_uint(d2.z), w2 = __float_as_uint(d2.w);
                 float Y = 0.f, UY = 0.f;
-                if (w0 >> 16) quad_run<kLS>(tab_s, lane2, w0, d1.z, k, Y, UY);
+                if (w0 >> 16) quad_run<kLS>(tab_s, lane, lim32, w0, d1.z, k, Y, UY);
                 if (w1 >> 16) {
-                    if (w1 & 2u) quad_run<kLL>(tab_s, lane2, w1, d2.x, k, Y, UY);
-                    else         quad_run<kSS>(tab_s, lane2, w1, d2.x, k, Y, UY);
+                    if (w1 & 2u) quad_run<kLL>(tab_s, lane, lim32, w1, d2.x, k, Y, UY);
+                    else         quad_run<kSS>(tab_s, lane, lim32, w1, d2.x, k, Y, UY);
                 }
-                if (w2 >> 16) quad_run<kSL>(tab_s, lane2, w2, d1.w, k, Y, UY);
+                if (w2 >> 16) quad_run<kSL>(tab_s, lane, lim32, w2, d1.w, k, Y, UY);
                 if (f == 0) { pY0 = Y; pUY0 = UY; }
                 else if (f == 1) pN1 = Y - UY;
                 else pN2 = Y - UY;

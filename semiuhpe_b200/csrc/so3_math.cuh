@@ -549,7 +549,7 @@ SUHPE_HD FamilyDesc make_family(float lo, float hi, float c, const float* utab, 
     d.scLS = div_rn(1.0f, sqrt_rn(d.fd));
     d.scSL = div_rn(1.0f, sqrt_rn(d.fs));
     d.scMid = (d.mid == kLL) ? d.scLS * d.scSL : 1.0f;
-    d.cut = cut_index(d.fd, d.fs, cl, cut_thr);
+    d.cut = cut_index(d.fd, d.fs, cl, cut_thr) & ~1;     // even: runs start on a node pair
     return d;
 }
 
@@ -561,31 +561,48 @@ SUHPE_HD void fisher_families(const float* s, const float* utab, const float* vt
 }
 
 // ----------------------------------------------------------------------------
-// Run words.  The thread that owns a sample packs each of the (up to) three runs of a family
-// into one word, laid out so that the warp that replays the quadrature decodes it with one mask and
-// one shift:
-//   bit  0     head: the run starts at the odd node of its first pair (slot 0 of the first pass is masked)
+// Run plan.  The warp that replays the quadrature works on node PAIRS (2m, 2m+1) in the halves of
+// packed registers, so the thread that owns a sample turns each family into
+//   * up to three pair-aligned runs [start, end), start and end even, every pair inside a run is
+//     fully valid and of the run's type -- so the replay needs one predicate per pair and no
+//     per-node masks;
+//   * up to four single "edge" nodes: where a type boundary b0 / b1 is odd, the pair (b-1, b)
+//     straddles two types; the owning thread evaluates its two nodes itself (scalar, node_typed)
+//     and adds them to the family's sums.  edge[0] = b0-1 as LS, edge[1] = b0 as mid,
+//     edge[2] = b1-1 as mid, edge[3] = b1 as SL; -1 = none (boundary even, node cut away, or the
+//     run it belongs to is empty).
+// A run is packed into one word that the warp decodes with one mask and one shift:
 //   bit  1     the middle run is LL (else SS)
 //   bits 4-12  16*m0: byte offset of the run's first node pair (start >> 1) in a float4 table column
-//   bits 16-25 slots: end - 2*m0, the number of node slots from the pair's first node to the run's
-//              end (0 = empty run); passes of 128 slots while more than 64 remain, then one of 64
+//   bits 16-24 the number of node pairs in the run (0 = empty run); passes of 64 pairs while more
+//              than 32 remain, then one of 32
 // ----------------------------------------------------------------------------
-SUHPE_HD uint32_t run_word(int lo, int end, int cut, bool mid_ll) {
-    const int start = lo > cut ? lo : cut;
+struct FamilyPlan { uint32_t word[3]; int edge[4]; };
+
+SUHPE_HD uint32_t run_word(int start, int end, bool mid_ll) {      // start, end even
     const uint32_t flag = mid_ll ? 2u : 0u;
     if (end <= start) return flag;
-    const int m0 = start >> 1;
-    return (uint32_t)(start & 1) | flag | ((uint32_t)m0 << 4) | ((uint32_t)(end - 2 * m0) << 16);
+    return flag | ((uint32_t)(start >> 1) << 4) | ((uint32_t)((end - start) >> 1) << 16);
 }
-SUHPE_HD unsigned run_word_head(uint32_t w) { return w & 1u; }
 SUHPE_HD bool run_word_mid_ll(uint32_t w) { return (w & 2u) != 0; }
 SUHPE_HD unsigned run_word_m0(uint32_t w) { return (w >> 4) & 511u; }
-SUHPE_HD int run_word_slots(uint32_t w) { return (int)(w >> 16); }
-SUHPE_HD void family_run_words(const FamilyDesc& d, uint32_t* w) {
-    w[0] = run_word(0, d.b0, d.cut, false);
-    w[1] = run_word(d.b0, d.b1, d.cut, d.mid == kLL);
-    w[2] = run_word(d.b1, kQuadNodes, d.cut, false);
+SUHPE_HD int run_word_pairs(uint32_t w) { return (int)(w >> 16); }
+
+SUHPE_HD void family_plan(const FamilyDesc& d, FamilyPlan& p) {
+    const int cut = d.cut, b0 = d.b0, b1 = d.b1;                   // cut even, 0 <= b0 <= b1 <= 512
+    const int up0 = (b0 + 1) & ~1, up1 = (b1 + 1) & ~1;
+    const int s_mid = up0 > cut ? up0 : cut, s_sl = up1 > cut ? up1 : cut;
+    p.word[0] = run_word(cut, b0 & ~1, false);
+    p.word[1] = run_word(s_mid, b1 & ~1, d.mid == kLL);
+    p.word[2] = run_word(s_sl, kQuadNodes, false);
+    const bool odd0 = (b0 & 1) != 0, odd1 = (b1 & 1) != 0;
+    const int lo_mid = b0 > cut ? b0 : cut;
+    p.edge[0] = (odd0 && b0 - 1 >= cut) ? b0 - 1 : -1;             // last node of the LS run
+    p.edge[1] = (odd0 && b0 >= cut && b0 < b1) ? b0 : -1;          // first node of the middle run
+    p.edge[2] = (odd1 && b1 - 1 >= lo_mid) ? b1 - 1 : -1;          // last node of the middle run
+    p.edge[3] = (odd1 && b1 >= cut) ? b1 : -1;                     // first node of the SL run (b1 odd => b1 <= 511)
 }
+SUHPE_HD int edge_type(const FamilyDesc& d, int k) { return k == 0 ? kLS : (k == 3 ? kSL : d.mid); }
 
 SUHPE_HD int node_type(const FamilyDesc& d, int i) {
     return i < d.b0 ? kLS : (i < d.b1 ? d.mid : kSL);

@@ -20,11 +20,12 @@ void emul_proper_svd(const float* A, long n, float* R, float* S, float* U, float
 
 }  // extern "C"
 
-// Mirrors the warp decomposition of the kernel: per family the 512 nodes split into up to
-// three runs of uniform type; a run is walked in passes of 64 nodes, lane l taking the adjacent
-// pair (2m, 2m+1), slots outside [start,end) zeroed; each lane keeps (lo,hi) partial sums of y
-// and u*y per run, scales them by the run's constant factor, and the warp butterfly-reduces
-// {Y0, UY0, N1, N2}.  The trapezoid end-point halves are subtracted afterwards.
+// Mirrors the warp decomposition of the kernel: per family the nodes [cut,512) split into up to
+// three pair-aligned runs of uniform type plus up to four single edge nodes (family_plan); a run is
+// walked in passes of 32 node pairs, lane l taking the pair (2m, 2m+1), pairs past the run's end
+// skipped; each lane keeps (lo,hi) partial sums of y and u*y per run, scales them by the run's
+// constant factor, and the warp butterfly-reduces {Y0, UY0, N1, N2}.  The edge nodes and the
+// trapezoid end-point halves are the owning thread's corrections.
 static float butterfly(float* v) {
     for (int off = 16; off >= 1; off >>= 1)
         for (int lane = 0; lane < 32; ++lane)
@@ -45,27 +46,26 @@ struct Tables {
 };
 static const Tables& tables() { static Tables t; return t; }
 
-// one run for one lane, walked exactly like quad_run/quad_pass: passes of 128 slots while more than
-// 64 remain, then one of 64; slot masks from (base, lenm); the run's factor applied at the end
+// one run for one lane, walked exactly like quad_run/quad_pass: passes of 64 pairs while more than
+// 32 remain, then one of 32; the lane's pair counts while `left` = pairs from its pair to the run's
+// end is positive; the run's factor applied at the end
 static void run_lane(const FamilyDesc& d, int type, uint32_t word, int lane, float* Y, float* UY) {
     const Tables& tb = tables();
-    const unsigned m0 = run_word_m0(word), head = run_word_head(word);
-    int slots = run_word_slots(word);
-    if (slots == 0) return;
-    const unsigned lenm = (unsigned)slots - head;
-    unsigned base = 2u * lane - head, m = m0;
+    int pairs = run_word_pairs(word);
+    if (pairs == 0) return;
+    unsigned m = run_word_m0(word);
+    int left = pairs - lane;
     float ylo = 0, yhi = 0, ulo = 0, uhi = 0;
-    while (slots > 0) {
-        const int W = slots > 64 ? 2 : 1;
+    while (pairs > 0) {
+        const int W = pairs > 32 ? 2 : 1;
         for (int w = 0; w < W; ++w) {
+            if (!(left > 32 * w)) continue;
             const int i0 = 2 * (int)(m + lane + 32 * w), i1 = i0 + 1;
-            float y0 = node_typed(d, type, tb.n[i0]), y1 = node_typed(d, type, tb.n[i1]);
-            if (!(base + 64u * w < lenm)) y0 = 0.f;
-            if (!(base + 64u * w + 1u < lenm)) y1 = 0.f;
+            const float y0 = node_typed(d, type, tb.n[i0]), y1 = node_typed(d, type, tb.n[i1]);
             ylo += y0; yhi += y1;
             ulo = fmaf(tb.n[i0].u, y0, ulo); uhi = fmaf(tb.n[i1].u, y1, uhi);
         }
-        slots -= 64 * W; m += 32 * W; base += 64 * W;
+        pairs -= 32 * W; m += 32 * W; left -= 32 * W;
     }
     const float sc = type_scale(d, type);
     *Y = fmaf(sc, ylo + yhi, *Y);
@@ -85,12 +85,12 @@ static void quadrature(const float* s, int cut_bits, float* F, float* N0, float*
     for (int lane = 0; lane < 32; ++lane) {
         for (int f = 0; f < 3; ++f) {
             const FamilyDesc& d = fam[f];
-            uint32_t w[3];
-            family_run_words(d, w);
+            FamilyPlan pl;
+            family_plan(d, pl);
             float Y = 0, UY = 0;
-            run_lane(d, kLS, w[0], lane, &Y, &UY);
-            run_lane(d, run_word_mid_ll(w[1]) ? kLL : kSS, w[1], lane, &Y, &UY);
-            run_lane(d, kSL, w[2], lane, &Y, &UY);
+            run_lane(d, kLS, pl.word[0], lane, &Y, &UY);
+            run_lane(d, run_word_mid_ll(pl.word[1]) ? kLL : kSS, pl.word[1], lane, &Y, &UY);
+            run_lane(d, kSL, pl.word[2], lane, &Y, &UY);
             if (f == 0) { pY0[lane] = Y; pUY0[lane] = UY; }
             else if (f == 1) pN1[lane] = Y - UY;
             else pN2[lane] = Y - UY;
@@ -101,18 +101,32 @@ static void quadrature(const float* s, int cut_bits, float* F, float* N0, float*
     const float f0 = fam[0].cut ? 0.f : end_node(fam[0], 0), l0 = end_node(fam[0], 511);
     const float f1 = fam[1].cut ? 0.f : end_node(fam[1], 0), l1 = end_node(fam[1], 511);
     const float f2 = fam[2].cut ? 0.f : end_node(fam[2], 0), l2 = end_node(fam[2], 511);
-    const float cY0 = 0.5f * (f0 + l0);
-    const float cUY0 = 0.5f * fmaf(uf, f0, ul * l0);
-    const float cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1));
-    const float cN2 = 0.5f * ((f2 + l2) - fmaf(uf, f2, ul * l2));
+    // edge nodes of the owning thread (same order as the kernel: family, then edge slot)
+    float eY[3], eUY[3];
+    for (int f = 0; f < 3; ++f) {
+        FamilyPlan pl;
+        family_plan(fam[f], pl);
+        eY[f] = eUY[f] = 0.f;
+        for (int k = 0; k < 4; ++k) {
+            if (pl.edge[k] < 0) continue;
+            const float y = end_node(fam[f], pl.edge[k]);
+            eY[f] += y;
+            eUY[f] = fmaf(tb.n[pl.edge[k]].u, y, eUY[f]);
+        }
+    }
+    const float cY0 = 0.5f * (f0 + l0) - eY[0];
+    const float cUY0 = 0.5f * fmaf(uf, f0, ul * l0) - eUY[0];
+    const float cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1)) - (eY[1] - eUY[1]);
+    const float cN2 = 0.5f * ((f2 + l2) - fmaf(uf, f2, ul * l2)) - (eY[2] - eUY[2]);
     *F = Y0 - cY0;
     *N0 = *F - (UY0 - cUY0);
     *N1 = n1 - cN1;
     *N2 = n2 - cN2;
 }
 
-// every node of [cut,512) must be covered exactly once by the passes the run words describe, with the
-// run type the reference's branch choice dictates, and no pass may reach past the padded tables
+// every node of [cut,512) must be covered exactly once -- by a pair of a run whose type is the one the
+// reference's branch choice dictates for BOTH nodes of the pair, or by an edge node of the right
+// type -- and no pass may reach past the padded tables
 extern "C" int emul_check_items(const float* S, long n, int cut_bits) {
     const Tables& tb = tables();
     int bad = 0;
@@ -120,27 +134,36 @@ extern "C" int emul_check_items(const float* S, long n, int cut_bits) {
         FamilyDesc fam[3];
         fisher_families(S + 3 * i, tb.u, tb.v, cut_bits, fam);
         for (int f = 0; f < 3; ++f) {
-            uint32_t w[3];
-            family_run_words(fam[f], w);
+            FamilyPlan pl;
+            family_plan(fam[f], pl);
+            if (fam[f].cut & 1) ++bad;
             int seen[512] = {};
             for (int r = 0; r < 3; ++r) {
-                const int type = r == 0 ? kLS : (r == 2 ? kSL : (run_word_mid_ll(w[r]) ? kLL : kSS));
-                const unsigned m0 = run_word_m0(w[r]), head = run_word_head(w[r]);
-                int slots = run_word_slots(w[r]);
-                if (slots == 0) continue;
+                const int type = r == 0 ? kLS : (r == 2 ? kSL : (run_word_mid_ll(pl.word[r]) ? kLL : kSS));
+                if (r == 1 && (run_word_mid_ll(pl.word[r]) ? kLL : kSS) != fam[f].mid) ++bad;
+                const unsigned m0 = run_word_m0(pl.word[r]);
+                const int pairs = run_word_pairs(pl.word[r]);
+                if (pairs == 0) continue;
                 unsigned m = m0;
                 int done = 0;
-                while (slots - done > 0) {
-                    const int W = (slots - done) > 64 ? 2 : 1;
+                while (pairs - done > 0) {
+                    const int W = (pairs - done) > 32 ? 2 : 1;
                     if (m + 32u * W > 288u) ++bad;
-                    m += 32 * W; done += 64 * W;
+                    m += 32 * W; done += 32 * W;
                 }
-                for (int t = (int)head; t < slots; ++t) {
+                for (int t = 0; t < 2 * pairs; ++t) {
                     const int node = 2 * (int)m0 + t;
                     if (node >= 512 || node < fam[f].cut) { ++bad; continue; }
                     ++seen[node];
                     if (node_type(fam[f], node) != type) ++bad;
                 }
+            }
+            for (int k = 0; k < 4; ++k) {
+                const int node = pl.edge[k];
+                if (node < 0) continue;
+                if (node >= 512 || node < fam[f].cut) { ++bad; continue; }
+                ++seen[node];
+                if (node_type(fam[f], node) != edge_type(fam[f], k)) ++bad;
             }
             for (int node = 0; node < 512; ++node)
                 if (seen[node] != (node >= fam[f].cut ? 1 : 0)) ++bad;
@@ -161,12 +184,9 @@ extern "C" void emul_cut_info(const float* S, long n, int cut_bits, int* cut, in
         for (int f = 0; f < 3; ++f) {
             cut[3 * i + f] = fam[f].cut;
             nv += 512 - fam[f].cut;
-            uint32_t w[3];
-            family_run_words(fam[f], w);
-            for (int r = 0; r < 3; ++r) {
-                const int slots = run_word_slots(w[r]);
-                ns += (slots + 63) / 64 * 64;
-            }
+            FamilyPlan pl;
+            family_plan(fam[f], pl);
+            for (int r = 0; r < 3; ++r) ns += (run_word_pairs(pl.word[r]) + 31) / 32 * 64;
         }
         valid[i] = nv; slots_exec[i] = ns;
     }
