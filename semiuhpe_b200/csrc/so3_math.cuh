@@ -812,10 +812,10 @@ SUHPE_HD void laplace_accum_scale(LaplaceAccum& a, float sc) {
 }
 
 SUHPE_HD void laplace_accum_point(LaplaceAccum& a, const float* A, float T, const float* r) {
-    float t = A[0] * r[0];
+    float t = fmaf(A[0], r[0], -T);          // -T rides in the first FMA: t = <A,R_k> - T
 #pragma unroll
     for (int i = 1; i < 9; ++i) t = fmaf(A[i], r[i], t);
-    const float d = T - t;
+    const float d = -t;
     const bool live = d >= kLapEps;          // clamp_min passes the gradient where input >= min
     float q, rs;
     sqrt_pair(fmaxf(d, kLapEps), q, rs);
