@@ -207,8 +207,11 @@ __device__ __forceinline__ void quad_pass(unsigned ta, int left, const RunConsts
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         const f2 y = mul2(mul2(pd[w], ps[w]), ex22(e[w]));
-        if (w == 0) acc_pair<0>(accY, accUY, y, u[w], left);
-        else        acc_pair<32>(accY, accUY, y, u[w], left);
+        if (w == 0) {
+            // a 64-pair pass only runs while more than 32 pairs remain: its first 32 are all inside
+            if (W == 2) { acc_add2(accY, y); acc_fma2(accUY, u[w], y); }
+            else acc_pair<0>(accY, accUY, y, u[w], left);
+        } else acc_pair<32>(accY, accUY, y, u[w], left);
     }
 }
 
@@ -373,7 +376,10 @@ fisher_fused_kernel(FisherArgs p) {
 
         // ---- phase 2: quadrature (warp per sample) ---------------------------
         float Y0 = 1.f, UY0 = 0.f, N1 = 0.f, N2 = 0.f;
-        const int lim32 = 32 - lane;
+        // lane constants of the run walk, laundered so they stay in registers (otherwise every run
+        // re-derives them from S2R SR_TID.X, a long-latency read at the head of its dependency chain)
+        int lane_r = lane, lim32 = 32 - lane;
+        asm volatile("" : "+r"(lane_r), "+r"(lim32));
 #pragma unroll 1
         for (int j = 0; j < count; ++j) {
             float pY0 = 0.f, pUY0 = 0.f, pN1 = 0.f, pN2 = 0.f;
@@ -388,12 +394,12 @@ fisher_fused_kernel(FisherArgs p) {
                 k.k2 = -(d0.y * kLog2e);
                 const uint32_t w0 = __float_as_uint(d2.y), w1 = __float_as_uint(d2.z), w2 = __float_as_uint(d2.w);
                 float Y = 0.f, UY = 0.f;
-                if (w0 >> 16) quad_run<kLS>(tab_s, lane, lim32, w0, d1.z, k, Y, UY);
+                if (w0 >> 16) quad_run<kLS>(tab_s, lane_r, lim32, w0, d1.z, k, Y, UY);
                 if (w1 >> 16) {
-                    if (w1 & 2u) quad_run<kLL>(tab_s, lane, lim32, w1, d2.x, k, Y, UY);
-                    else         quad_run<kSS>(tab_s, lane, lim32, w1, d2.x, k, Y, UY);
+                    if (w1 & 2u) quad_run<kLL>(tab_s, lane_r, lim32, w1, d2.x, k, Y, UY);
+                    else         quad_run<kSS>(tab_s, lane_r, lim32, w1, d2.x, k, Y, UY);
                 }
-                if (w2 >> 16) quad_run<kSL>(tab_s, lane, lim32, w2, d1.w, k, Y, UY);
+                if (w2 >> 16) quad_run<kSL>(tab_s, lane_r, lim32, w2, d1.w, k, Y, UY);
                 if (f == 0) { pY0 = Y; pUY0 = UY; }
                 else if (f == 1) pN1 = Y - UY;
                 else pN2 = Y - UY;
