@@ -290,6 +290,23 @@ def run_ours(args):
     k1.record()
     torch.cuda.synchronize()
     fused_ms = k0.elapsed_time(k1) / reps
+    # the same kernel with the negligible-node cut disabled (all 3 x 512 nodes of every rotation evaluated)
+    import semiuhpe_b200
+    prev_bits = semiuhpe_b200.set_quadrature_cut_bits(0)
+    try:
+        for _ in range(2):
+            fused()
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(5):
+            fused()
+        k1.record()
+        torch.cuda.synchronize()
+        fused_all_ms = k0.elapsed_time(k1) / 5
+    finally:
+        semiuhpe_b200.set_quadrature_cut_bits(prev_bits)
+    fused()                                              # leave the outputs of the default setting in place
+    torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
 
     thr = ws.read()[0]
@@ -321,7 +338,15 @@ def run_ours(args):
                        "has no FP32-pipe figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
         "algorithmic_flop_per_rotation": FLOP_PER_ROTATION, "rotations_per_launch": n, "kernel_ms": fused_ms,
         "kernel_share_of_step": fused_ms / (ms_total / args.steps),
-        "traffic": k2_traffic(n),
+        "traffic": (k2_traffic(n) or {}).get("bytes"), "traffic_detail": k2_traffic(n),
+        "negligible_node_cut": {
+            "bits": prev_bits,
+            "note": "nodes whose whole prefix is provably below 2^-bits of the normaliser sum are skipped (DESIGN.md K2; "
+                    "float64 proof test in tests/test_emul_math.py); `achieved` counts the algorithmic 69,120 FLOP per "
+                    "rotation either way",
+            "all_nodes_evaluated": {"kernel_ms": fused_all_ms,
+                                    "achieved": n * FLOP_PER_ROTATION / (fused_all_ms * 1e-3) / 1e12,
+                                    "frac": n * FLOP_PER_ROTATION / (fused_all_ms * 1e-3) / 1e12 / peak_tflops}},
         "hbm_view": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
                      "bytes_per_rotation": HBM_BYTES_PER_ROTATION,
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback"},

@@ -18,8 +18,12 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fish
     python profiles/run_kernels.py fisher 21 > $OUT/ncu_fisher.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'laplace|metrics|select|mask|hist|ce_close' -c 16 -f -o $OUT/others_full \
     python profiles/run_kernels.py others 21 > $OUT/ncu_others.log 2>&1
+# DRAM traffic of one K2 launch at the bench launch size (roofline.traffic)
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:fisher_fused -s 1 -c 1 --csv --log-file $OUT/k2_traffic.csv \
+    python profiles/run_kernels.py fisher 23 > $OUT/ncu_traffic.log 2>&1
+timeout 300 python profiles/time_fisher.py 23 > $OUT/time_fisher.log 2>&1
 timeout 300 python profiles/time_k4.py > $OUT/time_k4.log 2>&1
 timeout 300 python profiles/time_k2l.py > $OUT/time_k2l.log 2>&1
 timeout 300 python profiles/time_ce.py > $OUT/time_ce.log 2>&1
-cat $OUT/time_k4.log $OUT/time_k2l.log $OUT/time_ce.log
+cat $OUT/time_fisher.log $OUT/time_k4.log $OUT/time_k2l.log $OUT/time_ce.log; cat $OUT/k2_traffic.csv | tail -3
 tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; cat $OUT/bench.json; tail -3 $OUT/bench.err; cat $OUT/bench_ref.json

@@ -252,10 +252,24 @@ __device__ __forceinline__ NodeVals table_node(const QuadTables& tb, int i) {
     return n;
 }
 
+// One node evaluated by the thread that owns the sample (trapezoid end points, edge nodes): the
+// scalar twin of the packed run bodies.  Deliberately NOT inlined -- phase 1 calls it 18 times per
+// tile and the kernel's instruction footprint decides whether the 20 warps of a CTA, which sit in
+// different phases, keep hitting the instruction cache (arguments and result travel in registers).
+__device__ __noinline__ float node_value(int type, float fd, float fs, float ifd, float ifs, float k1L, float k1S, float k2,
+                                         float u, float v, float iu, float iv, float Lu, float Lv) {
+    FamilyDesc d;
+    d.fd = fd; d.fs = fs; d.ifd = ifd; d.ifs = ifs; d.k1L = k1L; d.k1S = k1S; d.k2 = k2;
+    NodeVals n;
+    n.u = u; n.v = v; n.iu = iu; n.iv = iv; n.Lu = Lu; n.Lv = Lv;
+    return node_typed(d, type, n);
+}
+__device__ __forceinline__ float node_scaled(const FamilyDesc& d, int t, const NodeVals& n) {
+    return node_value(t, d.fd, d.fs, d.ifd, d.ifs, d.k1L, d.k1S, d.k2, n.u, n.v, n.iu, n.iv, n.Lu, n.Lv) * type_scale(d, t);
+}
 // trapezoid half weight of an end node, with the constant factor of the run it sits in
 __device__ __forceinline__ float end_node(const FamilyDesc& d, int i, const NodeVals& n) {
-    const int t = node_type(d, i);
-    return node_typed(d, t, n) * type_scale(d, t);
+    return node_scaled(d, node_type(d, i), n);
 }
 
 }  // namespace
@@ -337,40 +351,42 @@ fisher_fused_kernel(FisherArgs p) {
             }
         }
         // trapezoid end-point corrections (weight 1/2 at nodes 0 and 511) and the parked descriptors
-        float cY0, cUY0, cN1, cN2;
+        // One family per trip of a ROLLED loop (the family's inputs are picked by selects): a third of
+        // the code of the unrolled form -- see node_value about the instruction footprint.
+        float cY0 = 0.f, cUY0 = 0.f, cN1 = 0.f, cN2 = 0.f;
         {
-            FamilyDesc fam[3];
-            fisher_families(s, reinterpret_cast<const float*>(tb.SSa), reinterpret_cast<const float*>(tb.SSa) + 2, p.cut_bits, fam);
-            float eY[3], eUY[3];                 // this thread's edge nodes (pairs that straddle a type boundary)
-#pragma unroll
+            const float* utab = reinterpret_cast<const float*>(tb.SSa);
+            const float cut_thr = cut_threshold(s, p.cut_bits);
+            const float uf = tb.first.u, ul = tb.last.u;
+#pragma unroll 1
             for (int f = 0; f < 3; ++f) {
-                const FamilyDesc& d = fam[f];
+                const FamilyDesc d = family_of(s, f, utab, utab + 2, cut_thr);
                 FamilyPlan pl;
                 family_plan(d, pl);
                 ws.desc[(f * 3 + 0) * 32 + lane] = make_float4(d.fd, d.fs, d.ifd, d.ifs);
                 ws.desc[(f * 3 + 1) * 32 + lane] = make_float4(d.k1L, d.k1S, d.scLS, d.scSL);
                 ws.desc[(f * 3 + 2) * 32 + lane] = make_float4(d.scMid, __uint_as_float(pl.word[0]), __uint_as_float(pl.word[1]), __uint_as_float(pl.word[2]));
-                eY[f] = 0.f; eUY[f] = 0.f;
-#pragma unroll
+                // this thread's edge nodes (pairs that straddle a type boundary)
+                float eY = 0.f, eUY = 0.f;
+#pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
-                    if (pl.edge[k] >= 0) {
-                        const NodeVals nv = table_node(tb, pl.edge[k]);
-                        const int t = edge_type(d, k);
-                        const float y = node_typed(d, t, nv) * type_scale(d, t);
-                        eY[f] += y;
-                        eUY[f] = fmaf(nv.u, y, eUY[f]);
+                    const int node = pl.edge[k];
+                    if (node >= 0) {
+                        const NodeVals nv = table_node(tb, node);
+                        const float y = node_scaled(d, edge_type(d, k), nv);
+                        eY += y;
+                        eUY = fmaf(nv.u, y, eUY);
                     }
                 }
+                // trapezoid half weights (node 0 is only corrected where it was evaluated: a family with
+                // cut > 0 skipped it), minus the edge nodes: what phase 3 subtracts from the warp's sums
+                const float f0 = d.cut ? 0.f : end_node(d, 0, tb.first), l0 = end_node(d, kQuadNodes - 1, tb.last);
+                const float cy = 0.5f * (f0 + l0) - eY;
+                const float cuy = 0.5f * fmaf(uf, f0, ul * l0) - eUY;
+                if (f == 0) { cY0 = cy; cUY0 = cuy; }
+                else if (f == 1) cN1 = cy - cuy;
+                else cN2 = cy - cuy;
             }
-            const float uf = tb.first.u, ul = tb.last.u;
-            // (node 0 is only corrected where it was evaluated: a family with cut > 0 skipped it)
-            const float f0 = fam[0].cut ? 0.f : end_node(fam[0], 0, tb.first), l0 = end_node(fam[0], kQuadNodes - 1, tb.last);
-            const float f1 = fam[1].cut ? 0.f : end_node(fam[1], 0, tb.first), l1 = end_node(fam[1], kQuadNodes - 1, tb.last);
-            const float f2v = fam[2].cut ? 0.f : end_node(fam[2], 0, tb.first), l2 = end_node(fam[2], kQuadNodes - 1, tb.last);
-            cY0 = 0.5f * (f0 + l0) - eY[0];
-            cUY0 = 0.5f * fmaf(uf, f0, ul * l0) - eUY[0];
-            cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1)) - (eY[1] - eUY[1]);
-            cN2 = 0.5f * ((f2v + l2) - fmaf(uf, f2v, ul * l2)) - (eY[2] - eUY[2]);
         }
         __syncwarp();
 

@@ -553,11 +553,17 @@ SUHPE_HD FamilyDesc make_family(float lo, float hi, float c, const float* utab, 
     return d;
 }
 
+// family k of a sample with proper singular values s (cut_thr = cut_threshold(s, bits))
+SUHPE_HD FamilyDesc family_of(const float* s, int k, const float* utab, const float* vtab, float cut_thr) {
+    const float lo = (k == 2) ? s[1] : s[2];
+    const float hi = (k == 0) ? s[1] : s[0];
+    const float c = (k == 0) ? s[0] + s[2] : s[1] + s[2];
+    return make_family(lo, hi, c, utab, vtab, cut_thr);
+}
 SUHPE_HD void fisher_families(const float* s, const float* utab, const float* vtab, int cut_bits, FamilyDesc* f) {
     const float thr = cut_threshold(s, cut_bits);
-    f[0] = make_family(s[2], s[1], s[0] + s[2], utab, vtab, thr);
-    f[1] = make_family(s[2], s[0], s[1] + s[2], utab, vtab, thr);
-    f[2] = make_family(s[1], s[0], s[1] + s[2], utab, vtab, thr);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f[k] = family_of(s, k, utab, vtab, thr);
 }
 
 // ----------------------------------------------------------------------------

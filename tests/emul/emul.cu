@@ -116,8 +116,8 @@ static void quadrature(const float* s, int cut_bits, float* F, float* N0, float*
     }
     const float cY0 = 0.5f * (f0 + l0) - eY[0];
     const float cUY0 = 0.5f * fmaf(uf, f0, ul * l0) - eUY[0];
-    const float cN1 = 0.5f * ((f1 + l1) - fmaf(uf, f1, ul * l1)) - (eY[1] - eUY[1]);
-    const float cN2 = 0.5f * ((f2 + l2) - fmaf(uf, f2, ul * l2)) - (eY[2] - eUY[2]);
+    const float cN1 = (0.5f * (f1 + l1) - eY[1]) - (0.5f * fmaf(uf, f1, ul * l1) - eUY[1]);
+    const float cN2 = (0.5f * (f2 + l2) - eY[2]) - (0.5f * fmaf(uf, f2, ul * l2) - eUY[2]);
     *F = Y0 - cY0;
     *N0 = *F - (UY0 - cUY0);
     *N1 = n1 - cN1;
