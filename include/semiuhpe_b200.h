@@ -89,6 +89,16 @@ int suhpe_fisher_ce_with_g1_f32(const float* A1, const float* G1, const float* A
  * mode 1 ("300WLP") out = (D aug_rot D pred^T)^T with D = diag(1,-1,-1).  All (n,9) row-major. */
 int suhpe_rotate_adjust_f32(const float* pred, const float* aug_rot, int64_t n, int32_t mode, float* out, void* stream);
 
+/* EMA / EMAN teacher update, SSLAgent.update_ema_variables (src/agent.py:277-299), for a list of
+ * `count` fp32 tensors in one call (the host arrays ema / src / numel are read before the call
+ * returns; the tensors are device memory):
+ *   mode 0 (config.eman, :293)  ema[i] = ema[i]*alpha + one_minus_alpha*src[i]   (products rounded, then added)
+ *   mode 1 (parameters, :298)   ema[i].mul_(alpha).add_(src[i], alpha=one_minus_alpha)   (fused multiply-add)
+ * alpha is the value AFTER the reference's warm-up rule (:278-283), already rounded to fp32 like ATen
+ * rounds a Python scalar; ema[i] and src[i] must not overlap. */
+int suhpe_ema_update_f32(float* const* ema, const float* const* src, const int64_t* numel, int32_t count,
+                         float alpha, float one_minus_alpha, int32_t mode, void* stream);
+
 /* K2 on given singular values: logC_F(S) and its backward G = dlogC/dS, entropy(S)
  * (src/fisher/torch_norm_factor.py:66-92 `logC_F`; S (n,3) sorted s1>=s2>=|s3| like every
  * reference call site).  Outputs nullable. */

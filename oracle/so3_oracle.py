@@ -521,6 +521,29 @@ def euler_from_matrices(R, full_range=False):
                         z * keep + zs * singular), dim=1)
 
 
+def update_ema_variables(net, ema_net, is_ema, alpha, global_step, eman=False):
+    """src/agent.py:277-299 restated line by line (torch CPU): the warm-up rule, then the EMAN blend over
+    the state_dict or the in-place EMA over the parameters."""
+    if is_ema:
+        alpha = min(1 - 1 / (global_step + 1), alpha)                     # :279-280
+    else:
+        alpha = 0                                                         # :283
+    with torch.no_grad():
+        if eman:                                                          # :286-293
+            state_dict_main, state_dict_ema = net.state_dict(), ema_net.state_dict()
+            for (k_main, v_main), (k_ema, v_ema) in zip(state_dict_main.items(), state_dict_ema.items()):
+                assert k_main == k_ema, "state_dict names are different!"
+                assert v_main.shape == v_ema.shape, "state_dict shapes are different!"
+                if 'num_batches_tracked' in k_ema:
+                    v_ema.copy_(v_main)
+                else:
+                    v_ema.copy_(v_ema * alpha + (1. - alpha) * v_main)
+        else:                                                             # :295-298
+            for ema_param, param in zip(ema_net.parameters(), net.parameters()):
+                ema_param.data.mul_(alpha).add_(param.detach(), alpha=1 - alpha)
+    return alpha
+
+
 def rotate_aug_adjust(pred_weak, aug_rot_mat, train_labeled):
     """src/agent.py:110-119, the same torch ops in the same order."""
     mat = pred_weak.clone().view(-1, 3, 3)

@@ -28,6 +28,7 @@ SIGNATURES = {
     "suhpe_fisher_ce_f32": (ctypes.c_int, [c_vp, c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_fisher_ce_with_g1_f32": (ctypes.c_int, [c_vp, c_vp, c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_rotate_adjust_f32": (ctypes.c_int, [c_vp, c_vp, i64, i32, c_vp, c_vp]),
+    "suhpe_ema_update_f32": (ctypes.c_int, [c_vp, c_vp, c_vp, i32, f32, f32, i32, c_vp]),
     "suhpe_laplace_nll_f32": (ctypes.c_int, [c_vp, c_vp, i64, c_vp, i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_select_init": (ctypes.c_int, [c_vp, u64, c_vp]),
     "suhpe_select_hist_f32": (ctypes.c_int, [c_vp, i64, i32, c_vp, c_vp, c_vp]),

@@ -113,6 +113,36 @@ def rotate_adjust(pred, aug_rot, mode):
     return out
 
 
+def ema_update(ema_tensors, src_tensors, alpha, mode):
+    """In-place EMA blend of a list of fp32 CUDA tensors (src/agent.py:293,298) in ceil(count/48)-ish
+    launches.  ``alpha`` is a Python float, rounded to fp32 here exactly like ATen rounds a Python scalar
+    multiplied into an fp32 tensor; so is ``1 - alpha`` (computed in double first, as the reference does)."""
+    ema_tensors, src_tensors = list(ema_tensors), list(src_tensors)
+    if len(ema_tensors) != len(src_tensors):
+        raise RuntimeError(f"ema_update: {len(ema_tensors)} teacher tensors against {len(src_tensors)} student tensors")
+    if not ema_tensors:
+        return
+    dev = ema_tensors[0].device
+    for e, s in zip(ema_tensors, src_tensors):
+        if not (e.is_cuda and s.is_cuda) or e.device != dev or s.device != dev:
+            raise RuntimeError("ema_update: every tensor must live on the same CUDA device (no CPU path)")
+        if e.dtype != torch.float32 or s.dtype != torch.float32:
+            raise TypeError("ema_update: fp32 tensors only (copy integer buffers with copy_)")
+        if e.shape != s.shape:
+            raise RuntimeError(f"ema_update: shape mismatch {tuple(e.shape)} vs {tuple(s.shape)}")
+        if not (e.is_contiguous() and s.is_contiguous()):
+            raise RuntimeError("ema_update: tensors must be contiguous (parameters and buffers are)")
+    count = len(ema_tensors)
+    PtrArr, NumArr = ctypes.c_void_p * count, ctypes.c_int64 * count
+    e_arr = PtrArr(*[e.data_ptr() for e in ema_tensors])
+    s_arr = PtrArr(*[s.data_ptr() for s in src_tensors])
+    n_arr = NumArr(*[e.numel() for e in ema_tensors])
+    a32 = ctypes.c_float(float(alpha)).value
+    oma32 = ctypes.c_float(1.0 - float(alpha)).value
+    with torch.cuda.device(dev):
+        check(lib().suhpe_ema_update_f32(e_arr, s_arr, n_arr, count, a32, oma32, int(mode), stream()), "ema_update")
+
+
 def fisher_from_s(S, *, logC=True, G=False, entropy=False):
     """K2 on given singular values (logC_F)."""
     S3 = as_records(S, "S", 3)

@@ -132,6 +132,33 @@ def unsupervised_terms(pred_weak, pred_strong, conf_thres, *, type_unsuper="ce",
     return out
 
 
+# ------------------------------------------------------------ 8f-4: EMA / EMAN teacher update
+def update_ema_variables(net, ema_net, is_ema, alpha, global_step, eman=False):
+    """``SSLAgent.update_ema_variables`` (src/agent.py:277-299) for a student ``net`` and its teacher
+    ``ema_net``: the warm-up rule ``alpha = min(1 - 1/(global_step+1), alpha)`` (``alpha = 0`` when
+    ``is_ema`` is false), then either the EMAN blend over the whole ``state_dict`` (``num_batches_tracked``
+    copied, :290-293) or the plain EMA over ``parameters()`` (:297-298) -- each a handful of multi-tensor
+    launches instead of two torch ops per tensor.  Returns the alpha that was applied."""
+    alpha = min(1 - 1 / (global_step + 1), alpha) if is_ema else 0
+    with torch.no_grad():
+        if eman:
+            main, ema = net.state_dict(), ema_net.state_dict()
+            e_list, s_list = [], []
+            for (k_main, v_main), (k_ema, v_ema) in zip(main.items(), ema.items()):
+                assert k_main == k_ema, "state_dict names are different!"
+                assert v_main.shape == v_ema.shape, "state_dict shapes are different!"
+                if "num_batches_tracked" in k_ema or v_ema.dtype != torch.float32:
+                    v_ema.copy_(v_main)                                   # integer counters (:290-291)
+                else:
+                    e_list.append(v_ema)
+                    s_list.append(v_main)
+            _ops.ema_update(e_list, s_list, alpha, 0)
+        else:
+            pairs = list(zip(ema_net.parameters(), net.parameters()))
+            _ops.ema_update([e.data for e, _ in pairs], [p.detach() for _, p in pairs], alpha, 1)
+    return alpha
+
+
 # ------------------------------------------------------------ a13..a16: metrics
 def rotate_aug_adjust(pred_weak, aug_rot_mat, train_labeled):
     """``pred_weak_adjusted`` of src/agent.py:110-122: the teacher's (b,9) parameters expressed in the

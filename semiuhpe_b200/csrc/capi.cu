@@ -267,6 +267,16 @@ int suhpe_rotate_adjust_f32(const float* pred, const float* aug_rot, int64_t n, 
     return rc(launch_rotate_adjust(pred, aug_rot, (long long)n, (int)mode, out, st(stream)));
 }
 
+int suhpe_ema_update_f32(float* const* ema, const float* const* src, const int64_t* numel, int32_t count,
+                         float alpha, float one_minus_alpha, int32_t mode, void* stream) {
+    if (count < 0 || mode < 0 || mode > 1 || (count > 0 && (!ema || !src || !numel))) return SUHPE_EINVAL;
+    for (int i = 0; i < count; ++i)
+        if (numel[i] < 0 || (numel[i] > 0 && (!ema[i] || !src[i]))) return SUHPE_EINVAL;
+    static_assert(sizeof(long long) == sizeof(int64_t), "numel table layout");
+    return rc(launch_ema_update(ema, src, reinterpret_cast<const long long*>(numel), (int)count, alpha, one_minus_alpha,
+                                (int)mode, st(stream)));
+}
+
 int suhpe_laplace_nll_f32(const float* A, const float* Rgt, int64_t n, const float* grid, int32_t N,
                           float* nll, float* grad, float* mode, float* logF, int* status, void* stream) {
     if (n < 0 || N <= 0 || (n > 0 && (!A || !Rgt || !grid || !nll))) return SUHPE_EINVAL;

@@ -91,6 +91,21 @@ cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream);
 cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream);
 cudaError_t launch_rotate_adjust(const float* P, const float* Raug, long long n, int mode, float* out, cudaStream_t stream);
 cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream);
+
+// EMA / EMAN teacher update (ema_kernels.cu): one launch carries up to kEmaMaxTensors tensors and
+// kEmaMaxBlocks CTAs of kEmaChunk elements each in its parameter block
+constexpr int kEmaMaxTensors = 48;
+constexpr int kEmaMaxBlocks = 320;
+constexpr int kEmaChunk = 32768;            // elements per CTA (a multiple of 4)
+struct EmaLaunch {
+    float* ema[kEmaMaxTensors];
+    const float* src[kEmaMaxTensors];
+    long long numel[kEmaMaxTensors];
+    int block_chunk[kEmaMaxBlocks];
+    unsigned char block_tensor[kEmaMaxBlocks];
+};
+cudaError_t launch_ema_update(float* const* ema, const float* const* src, const long long* numel, int count,
+                              float alpha, float one_minus_alpha, int mode, cudaStream_t stream);
 cudaError_t launch_metrics(MetricsArgs p, cudaStream_t stream);
 
 // ---- radix select over entropy keys -----------------------------------------

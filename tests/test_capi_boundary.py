@@ -43,6 +43,9 @@ def test_ctypes_table_matches_header(built):
     assert handle.suhpe_fisher_fused_f32(None, None, 5, 1.0, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_entropy_threshold_f32(None, 0, 0, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_laplace_nll_f32(None, None, 1, None, 0, None, None, None, None, None, None) == _capi.EINVAL
+    assert handle.suhpe_ema_update_f32(None, None, None, 3, 0.5, 0.5, 0, None) == _capi.EINVAL
+    assert handle.suhpe_ema_update_f32(None, None, None, 0, 0.5, 0.5, 2, None) == _capi.EINVAL
+    assert handle.suhpe_ema_update_f32(None, None, None, 0, 0.5, 0.5, 1, None) == 0        # empty list: nothing to launch
 
 
 def test_sass_is_sm100a_only(built):
@@ -57,6 +60,9 @@ def test_no_cpu_fallback(built):
     from semiuhpe_b200.fisher.fisher_utils import vmf_loss, fisher_entropy, batch_torch_A_to_R, fisher_CE
     from semiuhpe_b200.laplace.rotation_laplace import NLL_loss
     from semiuhpe_b200.agent import compute_err_deg_from_matrices, entropy_threshold, entropy_mask
+    from semiuhpe_b200.agent import update_ema_variables
+    with pytest.raises(RuntimeError):
+        update_ema_variables(torch.nn.Linear(3, 2), torch.nn.Linear(3, 2), True, 0.999, 10)
     A, R = torch.randn(4, 9), torch.eye(3).repeat(4, 1, 1)
     for call in (lambda: vmf_loss(A, R), lambda: fisher_entropy(A), lambda: batch_torch_A_to_R(A),
                  lambda: NLL_loss("RLaplace", A, R, R), lambda: compute_err_deg_from_matrices(R, R),
