@@ -435,6 +435,24 @@ def run_e2e(torch, dist, dev, n, args, world, rank):
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    # context for the number: the host link alone (one pinned -> device copy of the step's A and R_gt,
+    # nothing else running) -- the end-to-end leg cannot be faster than its H2D bytes over this rate
+    link = None
+    if world == 1:
+        d_A, d_R = torch.empty_like(A_h, device=dev), torch.empty_like(R_h, device=dev)
+        for _ in range(2):
+            d_A.copy_(A_h, non_blocking=True); d_R.copy_(R_h, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            d_A.copy_(A_h, non_blocking=True); d_R.copy_(R_h, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * (A_h.numel() + R_h.numel()) * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        link = {"h2d_gbs": h2d_gbs, "h2d_bound_rotations_per_s": h2d_gbs * 1e9 / 72.0,
+                "note": "pinned-host -> device copy of one step's inputs (72 B per rotation) timed alone"}
+        del d_A, d_R
     out = {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": res["h2d_bytes"],
            "d2h_bytes_per_step": res["d2h_bytes"], "steps": steps, "ms_per_step": 1e3 * dt / steps,
            "api": ("semiuhpe_b200.host_pipeline.FisherFilterPipeline.run -> "
@@ -443,6 +461,8 @@ def run_e2e(torch, dist, dev, n, args, world, rank):
            "threshold": res["threshold"], "kept": res["kept"],
            "note": "all ranks concurrently (they share the host's PCIe/memory system), max over ranks; global threshold"
                    if world > 1 else "single GPU"}
+    if link:
+        out["host_link"] = link
     pipe.close()
     return out
 

@@ -215,3 +215,32 @@ def test_negligible_node_cut_on_off(cuda, golden):
     S1 = full["S"].abs().sum(1)
     assert bool(((cut["entropy"] - full["entropy"]).abs() <= 2e-6 + 6e-7 * S1).all())
     assert grad_rel_err(cut["grad"].cpu().numpy(), full["grad"].cpu().numpy()).max() < 2e-6
+
+
+def test_scale_sweep_against_oracle(cuda):
+    """6,000 random parameter matrices over the scales the heads are trained at (singular values from
+    ~0.3 to ~60): every combination of run types, odd / even type boundaries (edge nodes), cut and uncut
+    families -- NLL, entropy, gradient and rotation against the oracle's fp32 restatement of the reference."""
+    from semiuhpe_b200.fisher.fisher_utils import vmf_loss, fisher_entropy
+    gen = torch.Generator().manual_seed(2024)
+    scales = torch.tensor([0.3, 1.0, 3.0, 5.0, 10.0, 20.0]).repeat_interleave(1000)
+    A = torch.randn(len(scales), 9, generator=gen) * scales[:, None]
+    R = random_rotations(len(scales), gen)
+    leaf = A.to(cuda).requires_grad_(True)
+    loss, Rest = vmf_loss(leaf, R.to(cuda), overreg=1.025)
+    loss.sum().backward()
+    ent = fisher_entropy(A.to(cuda))
+    ref_leaf = A.clone().requires_grad_(True)
+    ref_loss, ref_R = orc.vmf_loss(ref_leaf, R, overreg=1.025)
+    ref_loss.sum().backward()
+    ref_ent = orc.fisher_entropy(A)
+    assert_close(loss.detach().cpu().numpy(), ref_loss.detach().numpy(), RTOL, ATOL, "nll")
+    assert_close(ent.cpu().numpy(), ref_ent.numpy(), RTOL, 2 * ATOL, "entropy")
+    # gradients: 1e-5 away from singular-value degeneracies, 1e-4 near them (BASELINE north_star)
+    S = torch.linalg.svdvals(A.reshape(-1, 3, 3).double())
+    gap = torch.minimum(S[:, 0] - S[:, 1], S[:, 1] - S[:, 2]) / S[:, 0]
+    err = grad_rel_err(leaf.grad.cpu().numpy(), ref_leaf.grad.numpy())
+    assert err[(gap > 0.05).numpy()].max() < 1e-5 and err.max() < 1e-4
+    # rotation: conditioning ~ eps * s1 / (s2 + s3)
+    cond = (S[:, 0] / (S[:, 1] + S[:, 2]).clamp_min(1e-9)).numpy()
+    assert (np.abs(Rest.cpu().numpy() - ref_R.numpy()).reshape(len(scales), -1).max(1) <= 2e-6 * np.maximum(cond, 1.0) + 2e-6).all()
