@@ -60,9 +60,11 @@ int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float ov
                            float* S, float* G, uint64_t* hist, int* status, void* stream);
 
 /* Negligible-node cut of the K2 quadrature (process-wide setting; returns the previous value).
- * Every integrand of src/fisher/torch_norm_factor.py:33-63 is bounded by exp(-c(1-x)), so the
- * nodes far from x = 1 contribute less than 2^-bits of the normaliser sum in total; K2 skips
- * that provably negligible prefix.  Default 26 (a quarter of an fp32 ulp of the sum: below what
+ * Every integrand of src/fisher/torch_norm_factor.py:33-63 decays like exp(-c(1-x)) away from
+ * x = 1, so a prefix of the 512 nodes contributes less than 2^-bits of the normaliser sum in total;
+ * K2 skips that prefix where a per-sample bound PROVES it (rigorous upper bound of the prefix mass
+ * against a rigorous lower bound of the sum: cut_threshold / cut_index in csrc/so3_math.cuh, float64
+ * check in tests/test_emul_math.py).  Default 26 (an eighth of an fp32 ulp of the sum: below what
  * the reference's own fp32 torch.sum resolves); 0 evaluates all 512 nodes of every integral. */
 int suhpe_set_quadrature_cut_bits(int bits);
 

@@ -10,19 +10,20 @@
 //
 // Work decomposition (no tensor cores: nothing here is a dense contraction)
 //   phase 1  thread-per-sample : coalesced float4 tile load -> smem -> 9 regs, Hestenes SVD in
-//            registers, U/V parked in smem; per family the three uniform-type runs of the 512
-//            nodes, their constants and the negligible-node cut are derived ONCE by the owning
-//            thread and parked as 3 float4 (run words: so3_math.cuh)
-//   phase 2  warp-per-sample   : the warp replays the sample's runs; a pass covers 128 (or 64)
-//            consecutive node slots, lane l taking adjacent node pairs in the halves of f32x2
+//            registers, U/V parked in smem; per family the (up to) three pair-aligned runs of
+//            uniform type, their constants, the negligible-node cut and the edge nodes (pairs that
+//            straddle a type boundary) are derived ONCE by the owning thread; constants and run
+//            words parked as 3 float4 (family_plan: so3_math.cuh)
+//   phase 2  warp-per-sample   : the warp replays the sample's runs; a pass covers 64 (or 32)
+//            consecutive node pairs, lane l taking adjacent node pairs in the halves of f32x2
 //            registers.  Inside a run every node executes the same straight-line FFMA2 body: the
 //            large-argument Bessel branch needs no MUFU (1/u and log2 rsqrt(u) come from a
 //            shared-memory node table, 1/f and rsqrt(f) are per-sample constants), so one
-//            MUFU.EX2 per node is the only SFU work; slots outside a run are zeroed by selects
-//            on the ALU pipe
+//            MUFU.EX2 per node is the only SFU work; pairs past the end of a run (the tail of its
+//            last pass) are dropped by one select per pair on the ALU pipe
 //   phase 3  thread-per-sample : closing arithmetic, gradient
 //            -R_gt + overreg * U diag(g) V^T, entropy, staged float4 stores
-// Geometry: one persistent CTA of 20 warps per SM (<= 102 registers), 30 KB of node tables
+// Geometry: one persistent CTA of 20 warps per SM (90 registers), 28 KB of node tables
 // shared by the CTA + 9 KB of scratch per warp in dynamic shared memory.
 #include "kernels.cuh"
 #include "so3_math.cuh"
