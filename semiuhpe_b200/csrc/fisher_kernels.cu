@@ -23,8 +23,9 @@
 //            last pass) are dropped by one select per pair on the ALU pipe
 //   phase 3  thread-per-sample : closing arithmetic, gradient
 //            -R_gt + overreg * U diag(g) V^T, entropy, staged float4 stores
-// Geometry: one persistent CTA of 20 warps per SM (90 registers), 28 KB of node tables
-// shared by the CTA + 9 KB of scratch per warp in dynamic shared memory.
+// Geometry: one persistent CTA of 24 warps per SM (79 registers: the per-sample state of phase 3
+// rides through phase 2 in shared memory), 27 KB of node tables shared by the CTA + 8.25 KB of
+// scratch per warp in dynamic shared memory (225 KB).
 #include "kernels.cuh"
 #include "so3_math.cuh"
 #include <cstddef>
@@ -33,16 +34,20 @@ namespace suhpe {
 
 namespace {
 
-constexpr int kWarpsPerBlock = 20;
+#ifndef SUHPE_K2_WARPS
+#define SUHPE_K2_WARPS 24
+#endif
+constexpr int kWarpsPerBlock = SUHPE_K2_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 // per-warp shared scratch
 constexpr int kTileFloats = 32 * 9;              // one 32-sample tile of 3x3 records
 struct __align__(16) WarpScratch {
-    float a[kTileFloats];      // A in  -> gradient out
+    float a[kTileFloats];      // A in -> (phase 2) per-sample state s[3], <A,R_gt>, 4 sums -> gradient out; [sample*9 + k]
     float r[kTileFloats];      // R_gt in -> projected rotation out
-    float uv[18 * 32];         // U,V parked during the quadrature, [k][lane]
+    float uv[12 * 32];         // first two columns of U and of V parked during the quadrature, [k][lane]
+                               // (u2 = u0 x u1 is how the SVD defines it; v2 = v0 x v1 holds because det V = +1)
     float4 desc[9 * 32];       // 3 families x 3 float4 of run constants, [f*3+q][sample]
 };
 
@@ -348,7 +353,10 @@ fisher_fused_kernel(FisherArgs p) {
                 }
                 if (!proper_svd3(A, U, V, s)) bad = true;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) { ws.uv[k * 32 + lane] = U[k]; ws.uv[(9 + k) * 32 + lane] = V[k]; }
+                for (int i = 0; i < 3; ++i) {
+                    ws.uv[(2 * i) * 32 + lane] = U[3 * i]; ws.uv[(2 * i + 1) * 32 + lane] = U[3 * i + 1];
+                    ws.uv[(6 + 2 * i) * 32 + lane] = V[3 * i]; ws.uv[(7 + 2 * i) * 32 + lane] = V[3 * i + 1];
+                }
             }
         }
         // trapezoid end-point corrections (weight 1/2 at nodes 0 and 511) and the parked descriptors
@@ -389,10 +397,17 @@ fisher_fused_kernel(FisherArgs p) {
                 else cN2 = cy - cuy;
             }
         }
+        // Per-sample state that phase 3 needs rides through phase 2 in the thread's own nine slots of the
+        // (now consumed) A tile instead of in twelve registers: s, <A,R_gt>, and the four corrections,
+        // which the sample's lane turns into the corrected sums when its warp-sums arrive.
+        {
+            float* mine9 = ws.a + lane * 9;
+            mine9[0] = s[0]; mine9[1] = s[1]; mine9[2] = s[2]; mine9[3] = dot;
+            mine9[4] = cY0; mine9[5] = cUY0; mine9[6] = cN1; mine9[7] = cN2;
+        }
         __syncwarp();
 
         // ---- phase 2: quadrature (warp per sample) ---------------------------
-        float Y0 = 1.f, UY0 = 0.f, N1 = 0.f, N2 = 0.f;
         // lane constants of the run walk, laundered so they stay in registers (otherwise every run
         // re-derives them from S2R SR_TID.X, a long-latency read at the head of its dependency chain)
         int lane_r = lane, lim32 = 32 - lane;
@@ -422,15 +437,21 @@ fisher_fused_kernel(FisherArgs p) {
                 else pN2 = Y - UY;
             }
             pY0 = warp_sum(pY0); pUY0 = warp_sum(pUY0); pN1 = warp_sum(pN1); pN2 = warp_sum(pN2);
-            if (lane == j) { Y0 = pY0; UY0 = pUY0; N1 = pN1; N2 = pN2; }
+            if (lane == j) {                  // F, UY - c, N1, N2: sums minus this sample's corrections
+                float* mine9 = ws.a + lane * 9;
+                mine9[4] = pY0 - mine9[4]; mine9[5] = pUY0 - mine9[5]; mine9[6] = pN1 - mine9[6]; mine9[7] = pN2 - mine9[7];
+            }
         }
 
         // ---- phase 3: closing arithmetic + stores ----------------------------
         __syncwarp();
         if (mine) {
-            const float F = Y0 - cY0;
-            const float N0 = F - (UY0 - cUY0);
-            FisherStats st = fisher_finish(s, F, N0, N1 - cN1, N2 - cN2);
+            const float* mine9 = ws.a + lane * 9;
+            s[0] = mine9[0]; s[1] = mine9[1]; s[2] = mine9[2];
+            const float dot = mine9[3];
+            const float F = mine9[4];
+            const float N0 = F - mine9[5];
+            FisherStats st = fisher_finish(s, F, N0, mine9[6], mine9[7]);
             float U[9], V[9], M[9];
             const long long i = base + lane;
             if (p.nll) p.nll[i] = fmaf(p.overreg, st.logC, -dot);
@@ -440,7 +461,13 @@ fisher_fused_kernel(FisherArgs p) {
             if (p.G) { p.G[3 * i] = st.g[0]; p.G[3 * i + 1] = st.g[1]; p.G[3 * i + 2] = st.g[2]; }
             if (p.grad || p.Rout) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) { U[k] = ws.uv[k * 32 + lane]; V[k] = ws.uv[(9 + k) * 32 + lane]; }
+                for (int i = 0; i < 3; ++i) {
+                    U[3 * i] = ws.uv[(2 * i) * 32 + lane]; U[3 * i + 1] = ws.uv[(2 * i + 1) * 32 + lane];
+                    V[3 * i] = ws.uv[(6 + 2 * i) * 32 + lane]; V[3 * i + 1] = ws.uv[(7 + 2 * i) * 32 + lane];
+                }
+                // third columns: the cross product of the first two (the same expression proper_svd3 uses for u2)
+                U[2] = fmaf(U[3], U[7], -U[6] * U[4]); U[5] = fmaf(U[6], U[1], -U[0] * U[7]); U[8] = fmaf(U[0], U[4], -U[3] * U[1]);
+                V[2] = fmaf(V[3], V[7], -V[6] * V[4]); V[5] = fmaf(V[6], V[1], -V[0] * V[7]); V[8] = fmaf(V[0], V[4], -V[3] * V[1]);
             }
             if (p.grad) {
                 u_diag_vt(U, V, st.g[0], st.g[1], st.g[2], M);
@@ -757,7 +784,7 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     static_assert(kSmem <= 227 * 1024, "fisher_fused_kernel shared memory exceeds one SM");
     cudaError_t err = cudaFuncSetAttribute(fisher_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (err != cudaSuccess) return err;
-    // one persistent CTA of 20 warps per SM (the node tables are shared by the whole CTA); small
+    // one persistent CTA of 24 warps per SM (the node tables are shared by the whole CTA); small
     // batches get one sample per warp on as many SMs as that takes (latency)
     long long blocks = (p.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > sms) blocks = sms;
