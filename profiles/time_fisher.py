@@ -27,3 +27,15 @@ for bits in [int(b) for b in os.environ.get("BITS", "0,26").split(",")]:
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 10
     print(f"cut_bits={bits:2d}  {ms:8.3f} ms  {n/ms/1e3:9.1f} Mrot/s  {n*69120/ms/1e9:6.2f} TFLOP/s(alg)  nll.mean={nll.mean().item():.6f} ent.mean={ent.mean().item():.6f}")
+# forward-only NLL (no gradient, no entropy): the normaliser family alone
+semiuhpe_b200.set_quadrature_cut_bits(26)
+def run_fwd():
+    _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, 1.025, P(nll), None, None, None, None, None, None, None, None, S()), "f")
+for _ in range(3): run_fwd()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10): run_fwd()
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 10
+print(f"forward-only NLL  {ms:8.3f} ms  {n/ms/1e3:9.1f} Mrot/s  nll.mean={nll.mean().item():.6f}")

@@ -283,6 +283,9 @@ __device__ __forceinline__ float end_node(const FamilyDesc& d, int i, const Node
 // ---------------------------------------------------------------------------
 // K2: fused Fisher kernel
 // ---------------------------------------------------------------------------
+// NFAM = 3: the full head.  NFAM = 1: forward-only calls (NLL / logC without gradient, G or entropy --
+// validation under no_grad) need the normaliser family alone, a third of the quadrature.
+template <int NFAM>
 __global__ void __launch_bounds__(kThreads, 1)
 fisher_fused_kernel(FisherArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -368,7 +371,7 @@ fisher_fused_kernel(FisherArgs p) {
             const float cut_thr = cut_threshold(s, p.cut_bits);
             const float uf = tb.first.u, ul = tb.last.u;
 #pragma unroll 1
-            for (int f = 0; f < 3; ++f) {
+            for (int f = 0; f < NFAM; ++f) {
                 const FamilyDesc d = family_of(s, f, utab, utab + 2, cut_thr);
                 FamilyPlan pl;
                 family_plan(d, pl);
@@ -416,7 +419,7 @@ fisher_fused_kernel(FisherArgs p) {
         for (int j = 0; j < count; ++j) {
             float pY0 = 0.f, pUY0 = 0.f, pN1 = 0.f, pN2 = 0.f;
 #pragma unroll 1
-            for (int f = 0; f < 3; ++f) {
+            for (int f = 0; f < NFAM; ++f) {
                 const unsigned da = desc_s + 16u * (unsigned)(f * 96 + j);
                 const float4 d0 = lds128_ordered(da);
                 const float4 d1 = lds128_ordered(da + 512);
@@ -782,7 +785,9 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     const int sms = sm_count();
     constexpr size_t kSmem = sizeof(QuadTables) + sizeof(WarpScratch) * kWarpsPerBlock;
     static_assert(kSmem <= 227 * 1024, "fisher_fused_kernel shared memory exceeds one SM");
-    cudaError_t err = cudaFuncSetAttribute(fisher_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    const bool forward_only = !(p.grad || p.entropy || p.G);
+    auto kernel = forward_only ? fisher_fused_kernel<1> : fisher_fused_kernel<3>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (err != cudaSuccess) return err;
     // one persistent CTA of 24 warps per SM (the node tables are shared by the whole CTA); small
     // batches get one sample per warp on as many SMs as that takes (latency)
@@ -796,7 +801,7 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     p.samples_per_warp = (int)spw;
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     p.vec_ok = aligned(p.A) && aligned(p.Rgt) && aligned(p.grad) && aligned(p.Rout);
-    fisher_fused_kernel<<<(unsigned)blocks, kThreads, kSmem, stream>>>(p);
+    kernel<<<(unsigned)blocks, kThreads, kSmem, stream>>>(p);
     err = cudaGetLastError();
     // first radix-select pass over the entropies just written (they are still L2-resident)
     if (err == cudaSuccess && p.hist) err = launch_select_hist_accumulate(p.entropy, p.n, p.hist, stream);

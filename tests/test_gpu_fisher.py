@@ -236,6 +236,10 @@ def test_scale_sweep_against_oracle(cuda):
     ref_ent = orc.fisher_entropy(A)
     assert_close(loss.detach().cpu().numpy(), ref_loss.detach().numpy(), RTOL, ATOL, "nll")
     assert_close(ent.cpu().numpy(), ref_ent.numpy(), RTOL, 2 * ATOL, "entropy")
+    # forward-only launches (no gradient requested: one family of the quadrature) give the same NLL bit for bit
+    from semiuhpe_b200.fisher.fisher_utils import KL_Fisher
+    with torch.no_grad():
+        assert torch.equal(KL_Fisher(A.to(cuda), R.to(cuda), overreg=1.025), loss.detach())
     # gradients: 1e-5 away from singular-value degeneracies, 1e-4 near them (BASELINE north_star)
     S = torch.linalg.svdvals(A.reshape(-1, 3, 3).double())
     gap = torch.minimum(S[:, 0] - S[:, 1], S[:, 1] - S[:, 2]) / S[:, 0]
