@@ -32,3 +32,16 @@ torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 5
 print(f"K2L n=2^{n.bit_length() - 1} N={N} unroll={os.environ.get('SUHPE_LAP_UNROLL', '1')}: {ms:.3f} ms  {n / ms / 1e3:.1f} M rot/s  "
       f"{n * N * 50 / ms / 1e9:.2f} TFLOP/s at 50 FLOP/pair  nll.sum={nll.double().sum().item():.6f}")
+# forward-only (no gradient requested: validation under no_grad)
+call_f = lambda: _capi.check(lib.suhpe_laplace_nll_f32(P(A), P(R), n, P(grid), N, P(nll), None, P(mode), None, P(status), _capi.stream()), "laplace")
+ref = nll.clone()
+for _ in range(2):
+    call_f()
+torch.cuda.synchronize()
+a.record()
+for _ in range(5):
+    call_f()
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 5
+print(f"K2L forward only: {ms:.3f} ms  {n / ms / 1e3:.1f} M rot/s  max |nll - nll(full launch)| = {(ref - nll).abs().max().item():.2e}")

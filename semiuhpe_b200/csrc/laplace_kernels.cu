@@ -51,9 +51,12 @@ struct PackedSums { f2 z, c, m[9]; };
 __device__ __forceinline__ void acc_add2(f2& acc, f2 y) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(y)); }
 __device__ __forceinline__ void acc_fma2(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 
+template <bool GRAD>
 __device__ __forceinline__ void packed_scale(PackedSums& s, float sc) {
     const f2 k = dup(sc);
-    s.z = mul2(s.z, k); s.c = mul2(s.c, k);
+    s.z = mul2(s.z, k);
+    if (!GRAD) return;
+    s.c = mul2(s.c, k);
 #pragma unroll
     for (int i = 0; i < 9; ++i) s.m[i] = mul2(s.m[i], k);
 }
@@ -83,11 +86,13 @@ __device__ __forceinline__ PairRoots packed_roots(const float* A, float T, const
 }
 
 // second half: weights and sums, relative to the running minimum held as qminL = qmin * log2e
+template <bool GRAD>
 __device__ __forceinline__ void packed_sums(PackedSums& s, const PairRoots& o, float qminL, const f2* r) {
     float e0, e1;
     upk(fma2(o.nq, dup(kLog2e), dup(qminL)), e0, e1);
     const f2 w = mul2(pk(mufu_ex2(e0), mufu_ex2(e1)), o.rs);   // exp(p - c) / (-p)
     acc_add2(s.z, w);
+    if (!GRAD) return;                                         // forward only: the normaliser sum alone
     float c0, c1;
     upk(mul2(w, fma2(o.rs, o.rs, o.rs)), c0, c1);               // w (1/q + 1/q^2)
     const f2 cw = pk(o.live0 ? c0 : 0.0f, o.live1 ? c1 : 0.0f);
@@ -105,10 +110,12 @@ __device__ __forceinline__ void packed_sums(PackedSums& s, const PairRoots& o, f
 constexpr int kParkSlots = 23;
 constexpr int kStreamChunk = ((227 * 1024 - kParkSlots * kStreamThreads * 4) / 36) & ~3;   // grid points per smem chunk
 
+template <bool GRAD>
 __device__ __forceinline__ void park_fold(float* park, PackedSums& s, float qmin) {
     const float sc = mufu_ex2((qmin - park[11 * kStreamThreads]) * kLog2e);    // first fold: 2^-inf = 0
     float lo, hi;
     upk(s.z, lo, hi); park[0] = fmaf(park[0], sc, lo + hi); s.z = pk(0.f, 0.f);
+    if (!GRAD) { park[11 * kStreamThreads] = qmin; return; }
     upk(s.c, lo, hi); park[kStreamThreads] = fmaf(park[kStreamThreads], sc, lo + hi); s.c = pk(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -119,6 +126,9 @@ __device__ __forceinline__ void park_fold(float* park, PackedSums& s, float qmin
     park[11 * kStreamThreads] = qmin;
 }
 
+// GRAD = false: forward-only calls (no gradient requested: validation under no_grad) skip the eleven
+// gradient sums per point pair -- 17 packed ops instead of 28.
+template <bool GRAD>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 laplace_stream_kernel(LaplaceArgs p, int chunk) {
     extern __shared__ __align__(16) float gp[];      // [chunk/2][9][2]: point pairs interleaved per component
@@ -186,14 +196,14 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
                     upk(o0.nq, a0, a1); upk(o1.nq, b0, b1);
                     const float qm = -fmaxf(fmaxf(a0, a1), fmaxf(b0, b1));
                     if (qm < qmin) {                          // new running maximum of p = -q
-                        packed_scale(s, mufu_ex2((qm - qmin) * kLog2e));
+                        packed_scale<GRAD>(s, mufu_ex2((qm - qmin) * kLog2e));
                         qmin = qm;
                         qminL = qm * kLog2e;
                     }
-                    packed_sums(s, o0, qminL, r);
-                    packed_sums(s, o1, qminL, r + 9);
+                    packed_sums<GRAD>(s, o0, qminL, r);
+                    packed_sums<GRAD>(s, o1, qminL, r + 9);
                 }
-                park_fold(park, s, qmin);
+                park_fold<GRAD>(park, s, qmin);
             }
             if (groups * 4 < cn) {                            // up to 3 trailing points: scalar path, then merged
                 LaplaceAccum ta;
@@ -209,7 +219,7 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
                 s.z = pk(ta.z, 0.f); s.c = pk(ta.c, 0.f);
 #pragma unroll
                 for (int i = 0; i < 9; ++i) s.m[i] = pk(ta.m[i], 0.f);
-                park_fold(park, s, qmin);
+                park_fold<GRAD>(park, s, qmin);
             }
         }
 
@@ -346,11 +356,12 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     if (per_thread) {
         const int chunk = p.N < kStreamChunk ? ((p.N + 3) & ~3) : kStreamChunk;
         const size_t smem = ((size_t)chunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);
-        err = cudaFuncSetAttribute(laplace_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kernel = p.grad ? laplace_stream_kernel<true> : laplace_stream_kernel<false>;
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
         const long long tiles = (p.n + kStreamThreads - 1) / kStreamThreads;
         const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);    // one persistent CTA per SM
-        laplace_stream_kernel<<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
+        kernel<<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
     } else {
         const int chunk = p.N < kGridChunk ? p.N : kGridChunk;
         const int stride = (chunk + 3) & ~3;

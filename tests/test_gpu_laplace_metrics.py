@@ -60,6 +60,12 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
     big = _ops.laplace_nll(A, R, grids, grad=True, mode=True)
     small = _ops.laplace_nll(A[:300], R[:300], grids, grad=True, mode=True)
     assert_close(big["nll"][:300].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "decompositions")
+    # forward-only launch (no gradient requested: the gradient sums are not accumulated): the same NLL up to the
+    # last bit of the normaliser sum (without the gradient's second use of each weight, ptxas fuses the
+    # weight's multiply into the accumulate)
+    fwd = _ops.laplace_nll(A, R, grids, grad=False, mode=True)
+    assert_close(fwd["nll"].cpu().numpy(), big["nll"].cpu().numpy(), 5e-7, 2e-6, "forward-only")
+    assert torch.equal(fwd["mode"], big["mode"])
     assert grad_rel_err(big["grad"][:300].cpu().numpy(), small["grad"].cpu().numpy()).max() < 2e-4
     assert (big["mode"][:300] - small["mode"]).abs().max().item() < 1e-6
     idx = torch.arange(n - 64, n)
