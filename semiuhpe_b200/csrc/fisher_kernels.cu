@@ -334,31 +334,40 @@ fisher_fused_kernel(FisherArgs p) {
         const bool mine = lane < count;
 
         // ---- phase 1: load + SVD + run descriptors (thread per sample) ---------
+        // Small tiles (small batches, closing rounds: at most 10 samples in this warp) spread the work of a
+        // sample over three lanes, one family each -- phase 1 is a long dependent chain per lane and, with
+        // one sample per warp, the whole latency of a small launch (BASELINE configs 1-2).
+        const bool spread = NFAM == 3 && count <= 10;
+        const int sj = spread ? lane / 3 : lane;                  // the sample this lane sets up
+        const int fam0 = spread ? lane - 3 * sj : 0, fam1 = spread ? fam0 + 1 : NFAM;
+        const bool work = sj < count;
         float s[3] = {0.f, 0.f, 0.f};
         float dot = 0.f;
         if (p.Sin) {
             // logC_F entry: singular values given directly (torch_norm_factor.py:92), U = V = I
-            if (mine) {
-                const long long i = base + lane;
+            if (work) {
+                const long long i = base + sj;
                 s[0] = __ldg(p.Sin + 3 * i); s[1] = __ldg(p.Sin + 3 * i + 1); s[2] = __ldg(p.Sin + 3 * i + 2);
             }
         } else {
             load_tile(ws.a, p.A + base * 9, count, p.vec_ok, lane);
             if (p.Rgt) load_tile(ws.r, p.Rgt + base * 9, count, p.vec_ok, lane);
             __syncwarp();
-            if (mine) {
+            if (work) {
                 float A[9], U[9], V[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) A[k] = ws.a[lane * 9 + k];
+                for (int k = 0; k < 9; ++k) A[k] = ws.a[sj * 9 + k];
                 if (p.Rgt) {
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) dot = fmaf(A[k], ws.r[lane * 9 + k], dot);
+                    for (int k = 0; k < 9; ++k) dot = fmaf(A[k], ws.r[sj * 9 + k], dot);
                 }
-                if (!proper_svd3(A, U, V, s)) bad = true;
+                if (!proper_svd3(A, U, V, s)) bad = true;          // (the lanes of a spread sample repeat the SVD: no exchange needed)
+                if (fam0 == 0) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    ws.uv[(2 * i) * 32 + lane] = U[3 * i]; ws.uv[(2 * i + 1) * 32 + lane] = U[3 * i + 1];
-                    ws.uv[(6 + 2 * i) * 32 + lane] = V[3 * i]; ws.uv[(7 + 2 * i) * 32 + lane] = V[3 * i + 1];
+                    for (int i = 0; i < 3; ++i) {
+                        ws.uv[(2 * i) * 32 + sj] = U[3 * i]; ws.uv[(2 * i + 1) * 32 + sj] = U[3 * i + 1];
+                        ws.uv[(6 + 2 * i) * 32 + sj] = V[3 * i]; ws.uv[(7 + 2 * i) * 32 + sj] = V[3 * i + 1];
+                    }
                 }
             }
         }
@@ -371,13 +380,13 @@ fisher_fused_kernel(FisherArgs p) {
             const float cut_thr = cut_threshold(s, p.cut_bits);
             const float uf = tb.first.u, ul = tb.last.u;
 #pragma unroll 1
-            for (int f = 0; f < NFAM; ++f) {
+            for (int f = fam0; f < fam1; ++f) {
                 const FamilyDesc d = family_of(s, f, utab, utab + 2, cut_thr);
                 FamilyPlan pl;
                 family_plan(d, pl);
-                ws.desc[(f * 3 + 0) * 32 + lane] = make_float4(d.fd, d.fs, d.ifd, d.ifs);
-                ws.desc[(f * 3 + 1) * 32 + lane] = make_float4(d.k1L, d.k1S, d.scLS, d.scSL);
-                ws.desc[(f * 3 + 2) * 32 + lane] = make_float4(d.scMid, __uint_as_float(pl.word[0]), __uint_as_float(pl.word[1]), __uint_as_float(pl.word[2]));
+                ws.desc[(f * 3 + 0) * 32 + sj] = make_float4(d.fd, d.fs, d.ifd, d.ifs);
+                ws.desc[(f * 3 + 1) * 32 + sj] = make_float4(d.k1L, d.k1S, d.scLS, d.scSL);
+                ws.desc[(f * 3 + 2) * 32 + sj] = make_float4(d.scMid, __uint_as_float(pl.word[0]), __uint_as_float(pl.word[1]), __uint_as_float(pl.word[2]));
                 // this thread's edge nodes (pairs that straddle a type boundary)
                 float eY = 0.f, eUY = 0.f;
 #pragma unroll 1
@@ -400,13 +409,16 @@ fisher_fused_kernel(FisherArgs p) {
                 else cN2 = cy - cuy;
             }
         }
-        // Per-sample state that phase 3 needs rides through phase 2 in the thread's own nine slots of the
+        // Per-sample state that phase 3 needs rides through phase 2 in the sample's nine slots of the
         // (now consumed) A tile instead of in twelve registers: s, <A,R_gt>, and the four corrections,
-        // which the sample's lane turns into the corrected sums when its warp-sums arrive.
+        // which the sample's lane turns into the corrected sums when its warp-sums arrive.  (Every lane
+        // has read its A by now: the barrier orders those reads before the slots are overwritten.)
+        __syncwarp();
         {
-            float* mine9 = ws.a + lane * 9;
-            mine9[0] = s[0]; mine9[1] = s[1]; mine9[2] = s[2]; mine9[3] = dot;
-            mine9[4] = cY0; mine9[5] = cUY0; mine9[6] = cN1; mine9[7] = cN2;
+            float* mine9 = ws.a + sj * 9;
+            if (fam0 == 0) { mine9[0] = s[0]; mine9[1] = s[1]; mine9[2] = s[2]; mine9[3] = dot; mine9[4] = cY0; mine9[5] = cUY0; }
+            if (fam0 <= 1 && fam1 > 1) mine9[6] = cN1;
+            if (fam1 > 2) mine9[7] = cN2;
         }
         __syncwarp();
 
