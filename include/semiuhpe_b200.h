@@ -10,7 +10,7 @@
  *
  * The reference (hnuzhy/SemiUHPE) has no FFI: the path sits behind plain Python
  * functions.  Each entry point names the reference function(s) it replaces
- * (paths relative to the reference root); semiuhpe_b200/*.py mirrors those
+ * (paths relative to the reference root); the modules under semiuhpe_b200/ mirror those
  * Python signatures on top of this ABI and INTEGRATION.md shows the binding.
  *
  * Records: a rotation / parameter matrix is 9 contiguous fp32 (row-major 3x3).

@@ -48,6 +48,17 @@ def test_ctypes_table_matches_header(built):
     assert handle.suhpe_ema_update_f32(None, None, None, 0, 0.5, 0.5, 1, None) == 0        # empty list: nothing to launch
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (and as C++) on its own, warning-free."""
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "semiuhpe_b200.h"\nint main(void) { return suhpe_abi_version() < 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)]):
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        assert proc.returncode == 0, proc.stderr
+
+
 def test_sass_is_sm100a_only(built):
     from semiuhpe_b200 import _build
     out = subprocess.run(["cuobjdump", "-lelf", _build.LIB_PATH], capture_output=True, text=True).stdout
