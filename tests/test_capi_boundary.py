@@ -59,6 +59,26 @@ def test_header_is_plain_c(tmp_path):
         assert proc.returncode == 0, proc.stderr
 
 
+def test_c_host_links_and_calls_the_library(built, tmp_path):
+    """A plain C host program linked against the shared library (what a non-Python host does): version,
+    error strings and argument validation work without a GPU."""
+    from semiuhpe_b200 import _build
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "semiuhpe_b200.h"\n'
+        'int main(void) {\n'
+        '  printf("%d|%s|%s|", suhpe_abi_version(), suhpe_error_string(0), suhpe_error_string(SUHPE_EINVAL));\n'
+        '  printf("%d|", suhpe_fisher_fused_f32(NULL, NULL, 4, 1.0f, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL) == SUHPE_EINVAL);\n'
+        '  printf("%d\\n", suhpe_ema_update_f32(NULL, NULL, NULL, 0, 0.5f, 0.5f, 1, NULL));\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / "host"
+    lib_dir = os.path.dirname(_build.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-lsemiuhpe_b200", f"-Wl,-rpath,{lib_dir}"], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
+    assert out == "1|ok|invalid argument|1|0", out
+
+
 def test_sass_is_sm100a_only(built):
     from semiuhpe_b200 import _build
     out = subprocess.run(["cuobjdump", "-lelf", _build.LIB_PATH], capture_output=True, text=True).stdout
