@@ -260,7 +260,7 @@ __device__ __forceinline__ NodeVals table_node(const QuadTables& tb, int i) {
 
 // One node evaluated by the thread that owns the sample (trapezoid end points, edge nodes): the
 // scalar twin of the packed run bodies.  Deliberately NOT inlined -- phase 1 calls it 18 times per
-// tile and the kernel's instruction footprint decides whether the 20 warps of a CTA, which sit in
+// tile and the kernel's instruction footprint decides whether the 24 warps of a CTA, which sit in
 // different phases, keep hitting the instruction cache (arguments and result travel in registers).
 __device__ __noinline__ float node_value(int type, float fd, float fs, float ifd, float ifs, float k1L, float k1S, float k2,
                                          float u, float v, float iu, float iv, float Lu, float Lv) {
