@@ -37,6 +37,12 @@ namespace {
 #ifndef SUHPE_K2_WARPS
 #define SUHPE_K2_WARPS 24
 #endif
+#ifndef SUHPE_K2_RR
+#define SUHPE_K2_RR 1
+#endif
+#ifndef SUHPE_K2_BFLY
+#define SUHPE_K2_BFLY 1
+#endif
 constexpr int kWarpsPerBlock = SUHPE_K2_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -205,11 +211,41 @@ __device__ __forceinline__ void quad_pass(unsigned ta, int left, const RunConsts
             e[w] = fma2(dup(k.k2), v, mul2(dup(k.k1S), u[w]));
         }
     }
+#if SUHPE_K2_RR
+    // The 2W Horner chains advance one step each in turn (round robin): written this way the chains stay
+    // interleaved in the SASS -- evaluating one polynomial after the other left the last chain running
+    // alone for 8 dependent FFMA2s (4-5 cycles each against the pipe's 2), which the other warps of the
+    // scheduler do not always cover.  Same operations per chain, same order inside a chain: bit-identical.
+    {
+        constexpr bool dL = (T == kLL || T == kLS), sL = (T == kLL || T == kSL);
+        constexpr float cL[9] = {kLg8, kLg7, kLg6, kLg5, kLg4, kLg3, kLg2, kLg1, kLg0};
+        constexpr float cS[7] = {kSm6, kSm5, kSm4, kSm3, kSm2, kSm1, 1.0f};
+        f2 xd[W], xs[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            xd[w] = dL ? pd[w] : mul2(pd[w], pd[w]);
+            xs[w] = sL ? ps[w] : mul2(ps[w], ps[w]);
+            pd[w] = dup(dL ? cL[0] : cS[0]);
+            ps[w] = dup(sL ? cL[0] : cS[0]);
+        }
+#pragma unroll
+        for (int step = 1; step <= 8; ++step) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                if (dL) pd[w] = fma2(pd[w], xd[w], dup(cL[step]));
+                else if (step <= 6) pd[w] = fma2(pd[w], xd[w], dup(cS[step]));
+                if (sL) ps[w] = fma2(ps[w], xs[w], dup(cL[step]));
+                else if (step <= 6) ps[w] = fma2(ps[w], xs[w], dup(cS[step]));
+            }
+        }
+    }
+#else
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         pd[w] = (T == kLL || T == kLS) ? large2(pd[w]) : small2(pd[w]);
         ps[w] = (T == kLL || T == kSL) ? large2(ps[w]) : small2(ps[w]);
     }
+#endif
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         const f2 y = mul2(mul2(pd[w], ps[w]), ex22(e[w]));
@@ -321,15 +357,19 @@ fisher_fused_kernel(FisherArgs p) {
     // each), so every warp finishes together whatever n is (a plain round-robin of 32-sample tiles
     // costs a whole extra round for the leftover: 8 % at 2^20 samples).  Small batches are the
     // special case full_rounds = 0.
-    const long long warps_total = (long long)gridDim.x * kWarpsPerBlock;
-    const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    const int spw = p.samples_per_warp;
+    // (the tile's first sample index is 64-bit; it is re-derived where it is needed -- phase 1's loads and
+    // phase 3's stores -- instead of being carried through the quadrature, whose loop bodies want the registers)
+    auto tile_base = [&](int round_) -> long long {
+        const long long warps_total = (long long)gridDim.x * kWarpsPerBlock;
+        const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+        return round_ == (int)p.full_rounds ? p.full_rounds * warps_total * 32 + gwarp * p.samples_per_warp
+                                            : ((long long)round_ * warps_total + gwarp) * 32;
+    };
     bool bad = false;
 
-    for (long long round = 0; round <= p.full_rounds; ++round) {
-        const bool closing = round == p.full_rounds;
-        const long long base = closing ? p.full_rounds * warps_total * 32 + gwarp * spw : (round * warps_total + gwarp) * 32;
-        const int count = closing ? (int)max(0LL, min((long long)spw, p.n - base)) : 32;
+    for (int round = 0; round <= (int)p.full_rounds; ++round) {
+        long long base = tile_base(round);
+        const int count = round == (int)p.full_rounds ? (int)max(0LL, min((long long)p.samples_per_warp, p.n - base)) : 32;
         if (count == 0) break;
         const bool mine = lane < count;
 
@@ -451,15 +491,39 @@ fisher_fused_kernel(FisherArgs p) {
                 else if (f == 1) pN1 = Y - UY;
                 else pN2 = Y - UY;
             }
-            pY0 = warp_sum(pY0); pUY0 = warp_sum(pUY0); pN1 = warp_sum(pN1); pN2 = warp_sum(pN2);
-            if (lane == j) {                  // F, UY - c, N1, N2: sums minus this sample's corrections
-                float* mine9 = ws.a + lane * 9;
-                mine9[4] = pY0 - mine9[4]; mine9[5] = pUY0 - mine9[5]; mine9[6] = pN1 - mine9[6]; mine9[7] = pN2 - mine9[7];
+            if (!SUHPE_K2_BFLY) {
+                pY0 = warp_sum(pY0); pUY0 = warp_sum(pUY0); pN1 = warp_sum(pN1); pN2 = warp_sum(pN2);
+                if (lane == j) {                  // F, UY - c, N1, N2: sums minus this sample's corrections
+                    float* mine9 = ws.a + lane * 9;
+                    mine9[4] = pY0 - mine9[4]; mine9[5] = pUY0 - mine9[5]; mine9[6] = pN1 - mine9[6]; mine9[7] = pN2 - mine9[7];
+                }
+            } else if (NFAM == 1) {
+                pY0 = warp_sum(pY0);
+                if (lane == j) { float* mine9 = ws.a + lane * 9; mine9[4] = pY0 - mine9[4]; }
+            } else {
+                // Four warp sums in one butterfly: after the exchanges over lane bits 4 and 3 every lane carries
+                // ONE of the four quantities (index 2*bit4 + bit3), so 6 shuffles do the work of 20.  Lanes
+                // 0, 8, 16, 24 end up with the totals of F, UY, N1, N2 and subtract the sample's corrections in place.
+                const bool b4 = (lane_r & 16) != 0, b3 = (lane_r & 8) != 0;
+                float k0 = b4 ? pN1 : pY0, k1 = b4 ? pN2 : pUY0;
+                const float s0 = b4 ? pY0 : pN1, s1 = b4 ? pUY0 : pN2;
+                k0 += __shfl_xor_sync(kFull, s0, 16);
+                k1 += __shfl_xor_sync(kFull, s1, 16);
+                float t = b3 ? k1 : k0;
+                t += __shfl_xor_sync(kFull, b3 ? k0 : k1, 8);
+                t += __shfl_xor_sync(kFull, t, 4);
+                t += __shfl_xor_sync(kFull, t, 2);
+                t += __shfl_xor_sync(kFull, t, 1);
+                if ((lane_r & 7) == 0) {
+                    float* slot = ws.a + j * 9 + 4 + (lane_r >> 3);
+                    *slot = t - *slot;
+                }
             }
         }
 
         // ---- phase 3: closing arithmetic + stores ----------------------------
         __syncwarp();
+        { int r_ = round; asm volatile("" : "+r"(r_)); base = tile_base(r_); }
         if (mine) {
             const float* mine9 = ws.a + lane * 9;
             s[0] = mine9[0]; s[1] = mine9[1]; s[2] = mine9[2];

@@ -28,6 +28,9 @@ namespace suhpe {
 
 namespace {
 
+#ifndef SUHPE_K2L_NEWTON
+#define SUHPE_K2L_NEWTON 1
+#endif
 constexpr int kLapThreads = 256;
 constexpr int kGridChunk = 4608;           // grid points resident in shared memory at once
 constexpr unsigned kFull = 0xffffffffu;
@@ -81,7 +84,15 @@ __device__ __forceinline__ PairRoots packed_roots(const float* A, float T, const
     const f2 nd = pk(n0, n1);
     o.rs = pk(mufu_rsqrt(-n0), mufu_rsqrt(-n1));
     const f2 nq = mul2(nd, o.rs);
+#if SUHPE_K2L_NEWTON
     o.nq = fma2(mul2(o.rs, dup(0.5f)), fma2(nq, nq, nd), nq);
+#else
+    // q = d * rsqrt(d) as MUFU.RSQ delivers it (<= 2^-22.4 relative): the exponent (qmin - q) log2(e) moves by
+    // < 4e-6 for q <= 20, the weights by the same relative amount -- an order of magnitude below the
+    // reference's own fp32 noise on this path -- and the Newton step's three packed ops per
+    // point pair (11 % of the loop's FMA-pipe work) are not spent
+    o.nq = nq;
+#endif
     return o;
 }
 
