@@ -227,8 +227,9 @@ def run_ours(args):
     P, S = _capi.ptr, _capi.stream
     launches = [0]
 
-    def fused():
-        _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, OVERREG, P(nll), P(grad), None, P(ent), None, None, None,
+    def fused(bits=_capi.CUT_BITS_DEFAULT):
+        # K2 counts the first radix digit of every entropy itself (hist): one launch
+        _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, OVERREG, bits, P(nll), P(grad), None, P(ent), None, None, None,
                                                P(ws.hist[0]), P(status), S()), "fused")
         launches[0] += 1
 
@@ -291,31 +292,31 @@ def run_ours(args):
     torch.cuda.synchronize()
     fused_ms = k0.elapsed_time(k1) / reps
     # the same kernel with the negligible-node cut disabled (all 3 x 512 nodes of every rotation evaluated)
-    import semiuhpe_b200
-    prev_bits = semiuhpe_b200.set_quadrature_cut_bits(0)
-    try:
-        for _ in range(2):
-            fused()
-        torch.cuda.synchronize()
-        k0.record()
-        for _ in range(5):
-            fused()
-        k1.record()
-        torch.cuda.synchronize()
-        fused_all_ms = k0.elapsed_time(k1) / 5
-    finally:
-        semiuhpe_b200.set_quadrature_cut_bits(prev_bits)
-    fused()                                              # leave the outputs of the default setting in place
+    prev_bits = _capi.CUT_BITS_DEFAULT
+    for _ in range(2):
+        fused(0)
     torch.cuda.synchronize()
+    k0.record()
+    for _ in range(5):
+        fused(0)
+    k1.record()
+    torch.cuda.synchronize()
+    fused_all_ms = k0.elapsed_time(k1) / 5
     clocks = sampler.stop() if sampler else None
+    ws.hist.zero_()
+    kept.zero_()
+    step()                                               # leave the outputs of one default-setting step in place
+    torch.cuda.synchronize()
 
     thr = ws.read()[0]
     kept_n = int(kept.item())
     assert int(status.item()) == 0 and bool(torch.isfinite(nll).all()) and bool(torch.isfinite(ent).all())
     value = n_total * args.steps / (ms_total * 1e-3)
+    # parity of the (all-gathered) radix select against a sort of the concatenated pool (src/agent.py:403-407)
+    check_dev = threshold_check(torch, dist, dev, world, rank, ent, thr, kept_n, k)
 
     # end-to-end leg on every rank at once (they share the host's PCIe/memory system), max over ranks
-    e2e = None if args.no_e2e else run_e2e(torch, dist, dev, n, args, world, rank)
+    e2e = None if args.no_e2e else run_e2e(torch, dist, dev, n, args, world, rank, k)
 
     if rank != 0:
         if world > 1:
@@ -358,6 +359,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic", "config": workload_config(world, n),
         "clocks": clocks, "e2e": e2e, "gpu_launches": step_launches, "roofline": roofline,
         "threshold": thr, "kept": kept_n,
+        "threshold_check": {"device": check_dev, "e2e": (e2e or {}).pop("threshold_check", None)},
     }
     if world == 1 and not args.no_cpu:
         v, cores, secs = time_cpu(args.cpu_sample, 1)
@@ -367,7 +369,7 @@ def run_ours(args):
                       "(torch-CPU restatement of the reference: vmf_loss fwd+bwd, fisher_entropy, numpy sort + mask), "
                       "all host threads"}
     if world == 1 and not args.skip_extra:
-        line["extra"] = side_configs(torch, dev, _ops)
+        line["extra"] = side_configs(torch, dev, _ops, peak_tflops, hbm_peak, with_cpu=not args.no_cpu)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -410,7 +412,36 @@ def fp32_probe(torch, lib, dev, _capi):
     return out
 
 
-def run_e2e(torch, dist, dev, n, args, world, rank):
+def threshold_check(torch, dist, dev, world, rank, ent, thr, kept_local, k):
+    """Driver-visible parity of the threshold: every rank must hold the bit-identical value, and it must equal
+    ``sort(concat(all shards))[k]`` with ``sum(kept) == count(e < thr)`` (src/agent.py:403-407,148).  The
+    entropies of every rank are all-gathered (268 MB at 8 x 2^23) and sorted with torch.sort on the device."""
+    import struct
+    bits = struct.unpack("<i", struct.pack("<f", thr))[0]
+    mine = torch.tensor([bits, kept_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        every = torch.empty((world, 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, mine.reshape(1, 2))
+        pool = torch.empty((world, ent.numel()), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(pool, ent.reshape(1, -1).contiguous())
+    else:
+        every, pool = mine.reshape(1, 2), ent.reshape(1, -1)
+    same = bool((every[:, 0] == every[0, 0]).all())
+    kept_sum = int(every[:, 1].sum())
+    out = {"ranks": world, "n_total": int(pool.numel()), "k": int(k), "identical_on_all_ranks": same,
+           "kept_sum": kept_sum}
+    if rank == 0:
+        flat = pool.reshape(-1)
+        ref = torch.sort(flat).values[k]
+        below = int((flat < ref).sum())
+        out.update(sorted_k=float(ref), equals_sorted_k=bool(ref.view(torch.int32) == bits),
+                   kept_equals_count_below=bool(kept_sum == below), count_below=below)
+        assert same and out["equals_sorted_k"] and out["kept_equals_count_below"], out
+    del pool
+    return out
+
+
+def run_e2e(torch, dist, dev, n, args, world, rank, k):
     """Same step through the C ABI's host-buffer entry: pinned host A/R -> H2D -> K2/K3 -> D2H."""
     from semiuhpe_b200.host_pipeline import FisherFilterPipeline
     gen = torch.Generator().manual_seed(77 + rank)
@@ -463,14 +494,18 @@ def run_e2e(torch, dist, dev, n, args, world, rank):
                    if world > 1 else "single GPU"}
     if link:
         out["host_link"] = link
+    out["threshold_check"] = threshold_check(torch, dist, dev, world, rank, res["entropy"].to(dev), res["threshold"],
+                                             res["kept"], k)
     pipe.close()
     return out
 
 
-def side_configs(torch, dev, _ops):
-    """Device-timed side numbers for BASELINE configs 1-4 (parity-test cases, reported for context)."""
+def side_configs(torch, dev, _ops, fp32_peak_tflops, hbm_peak_gbs, with_cpu=True):
+    """BASELINE configs 1-4 (parity-test cases, reported for context): device-timed numbers, their roofline
+    fractions where a roofline applies (C3: FP32 pipe, C4: HBM), and the reference's CPU algorithm (oracle port)
+    timed on this box's host cores in the same run, bounded samples."""
     import semiuhpe_b200
-    from semiuhpe_b200.agent import dynamic_entropy_filter, _quat_to_matrix
+    from semiuhpe_b200.agent import dynamic_entropy_filter, _quat_to_matrix, ssl_loss, unsupervised_terms
     from semiuhpe_b200.fisher.fisher_utils import vmf_loss
     out = {}
 
@@ -486,31 +521,68 @@ def side_configs(torch, dev, _ops):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
+    def graphed(fn):
+        """fn captured once into a CUDA graph (warm-up on the capture stream first: handles, workspaces and
+        kernel attributes are created outside the capture); returns the replay callable."""
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+        return g.replay
+
     gen = torch.Generator(device=dev).manual_seed(5)
     rot = lambda m: _quat_to_matrix(torch.nn.functional.normalize(torch.randn(m, 4, device=dev, generator=gen), dim=1)).contiguous()
     A32, R32 = 10 * torch.randn(32, 9, device=dev, generator=gen), rot(32)
     A128 = 10 * torch.randn(128, 9, device=dev, generator=gen)
+    S128 = A128 + 0.5
+    leaf32 = A32.clone().requires_grad_(True)
+    leaf128 = S128.clone().requires_grad_(True)
 
     def c1():
-        leaf = A32.clone().requires_grad_(True)
-        loss, _ = vmf_loss(leaf, R32, overreg=OVERREG)
+        leaf32.grad = None
+        loss, _ = vmf_loss(leaf32, R32, overreg=OVERREG)
         loss.mean().backward()
+
+    def c1_one_call():
+        leaf32.grad = None
+        ssl_loss(leaf32, R32, overreg=OVERREG)[0].backward()
 
     def c2():
         c1()
         dynamic_entropy_filter(A128, LEFT_RATIO, return_threshold=False)
 
-    def c2_ssl():
-        # the whole SSL step of BASELINE config 2 with the default unsupervised loss (type_unsuper 'ce'):
+    def c2_ssl_mirrors():
+        # the whole SSL step of BASELINE config 2 through the per-function mirrors (type_unsuper 'ce'):
         # supervised NLL fwd+bwd on 32 + entropy/mask/fisher_CE fwd+bwd on 128, no host sync
-        from semiuhpe_b200.agent import unsupervised_terms
         c1()
-        strong = (A128 + 0.5).requires_grad_(True)
-        unsupervised_terms(A128, strong, -3.6, type_unsuper="ce")["unsuper_loss"].backward()
+        leaf128.grad = None
+        unsupervised_terms(A128, leaf128, -3.6, type_unsuper="ce")["unsuper_loss"].backward()
 
-    out["c1_fisher_b32_fwd_bwd_us"] = 1e3 * timed(c1, 50)
-    out["c2_teacher_step_32_128_us"] = 1e3 * timed(c2, 50)
-    out["c2_ssl_step_ce_32_128_us"] = 1e3 * timed(c2_ssl, 50)
+    def c2_ssl_one_call():
+        # the same loss head as ONE C call (suhpe_ssl_step_f32) + its backward
+        leaf32.grad = None
+        leaf128.grad = None
+        ssl_loss(leaf32, R32, A128, leaf128, -3.6, SSL_lambda=1.0, type_unsuper="ce", overreg=OVERREG)[0].backward()
+
+    out["c1_fisher_b32_fwd_bwd_us"] = 1e3 * timed(c1, 100)
+    out["c1_fisher_b32_fwd_bwd_one_call_us"] = 1e3 * timed(c1_one_call, 100)
+    out["c2_teacher_step_32_128_us"] = 1e3 * timed(c2, 100)
+    out["c2_ssl_step_ce_32_128_mirrors_us"] = 1e3 * timed(c2_ssl_mirrors, 100)
+    out["c2_ssl_step_ce_32_128_us"] = 1e3 * timed(c2_ssl_one_call, 100)
+    try:
+        out["c1_fisher_b32_fwd_bwd_graph_us"] = 1e3 * timed(graphed(c1), 200)
+        out["c2_ssl_step_ce_32_128_graph_us"] = 1e3 * timed(graphed(c2_ssl_one_call), 200)
+    except Exception as exc:                               # a capture failure must not take the bench line down
+        out["graph_capture_error"] = f"{type(exc).__name__}: {exc}"[:300]
+        torch.cuda.synchronize()
+    out["small_batch_note"] = ("wall time per step in a tight loop (CUDA events over 100 steps: the larger of host launch cost "
+                               "and device time); *_graph_us = the same Python step captured once in a CUDA graph and replayed")
     nce = 1 << 22
     Ace1 = 10 * torch.randn(nce, 9, device=dev, generator=gen)
     Ace2 = Ace1 + 2 * torch.randn(nce, 9, device=dev, generator=gen)
@@ -525,12 +597,90 @@ def side_configs(torch, dev, _ops):
     out["c3_laplace_2p20_N4608_ms"] = ms
     out["c3_laplace_rot_per_s"] = n3 / (ms * 1e-3)
     out["c3_laplace_tflops_at_230400_flop"] = n3 * 230400 / (ms * 1e-3) / 1e12
+    out["c3_roofline"] = {"bound": "fp32", "achieved": out["c3_laplace_tflops_at_230400_flop"], "peak": fp32_peak_tflops,
+                          "unit": "TFLOP/s", "frac": out["c3_laplace_tflops_at_230400_flop"] / fp32_peak_tflops,
+                          "algorithmic_flop_per_rotation": 230400}
     n4 = 10_000_000
     Rp, Rg = rot(n4), rot(n4)
     ge = (torch.rand(n4, 3, device=dev, generator=gen) * 2 - 1) * 89
     ms = timed(lambda: _ops.so3_metrics(Rp, Rg, ge, geo=True, frob=True, abs_err=True, sums=True), 5)
     out["c4_metrics_10M_ms"] = ms
     out["c4_metrics_gbs_at_104B"] = n4 * 104 / (ms * 1e-3) / 1e9
+    out["c4_roofline"] = {"bound": "hbm", "achieved": out["c4_metrics_gbs_at_104B"], "peak": hbm_peak_gbs, "unit": "GB/s",
+                          "frac": out["c4_metrics_gbs_at_104B"] / hbm_peak_gbs, "algorithmic_bytes_per_pair": 104}
+    if with_cpu:
+        cpu = side_cpu_baselines(torch, A32.cpu(), R32.cpu(), A128.cpu(), S128.cpu(), A3[:256].cpu(), R3[:256].cpu(), grid.cpu(),
+                                 Rp[:1_000_000].cpu(), Rg[:1_000_000].cpu(), ge[:20_000].cpu())
+        out["cpu_baseline"] = cpu
+        out["c1_speedup_vs_cpu"] = cpu["c1_fisher_b32_fwd_bwd_us"] / out["c1_fisher_b32_fwd_bwd_us"]
+        out["c2_ssl_speedup_vs_cpu"] = cpu["c2_ssl_step_ce_32_128_us"] / out["c2_ssl_step_ce_32_128_us"]
+        out["c3_speedup_vs_cpu"] = out["c3_laplace_rot_per_s"] / cpu["c3_laplace_rot_per_s"]
+        out["c4_speedup_vs_cpu"] = (n4 / (out["c4_metrics_10M_ms"] * 1e-3)) / cpu["c4_metrics_pairs_per_s"]
+    return out
+
+
+def side_cpu_baselines(torch, A32, R32, A128, S128, A3, R3, grid, Rp, Rg, ge):
+    """The reference's CPU algorithm (oracle/so3_oracle.py, torch CPU, pinned by golden vectors generated from
+    the live reference) for BASELINE configs 1-4 on this host: C1/C2 at full size, C3 on a 256-rotation chunk
+    (the reference materialises (b,N,3,3): 166 KB per rotation plus autograd copies), C4 geodesic on 10^6 pairs
+    and the per-sample Python Euler loop of src/utils.py:240-242 on 2*10^4 -- rates, stated as such."""
+    from oracle import so3_oracle as orc
+    import numpy as np
+    cores = torch.get_num_threads()
+
+    def best(fn, reps):
+        fn()
+        t = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            t = dt if t is None else min(t, dt)
+        return t
+
+    def c1():
+        leaf = A32.clone().requires_grad_(True)
+        loss, _ = orc.vmf_loss(leaf, R32, overreg=OVERREG)
+        loss.mean().backward()
+
+    def c2_teacher():
+        c1()
+        with torch.no_grad():
+            ent = orc.fisher_entropy(A128)
+        thr, _ = orc.pool_threshold(ent.numpy(), LEFT_RATIO)
+        orc.keep_mask(ent, float(thr))
+
+    def c2_ssl():
+        c1()
+        with torch.no_grad():
+            ent = orc.fisher_entropy(A128)
+        mask, _ = orc.keep_mask(ent, -3.6)
+        strong = S128.clone().requires_grad_(True)
+        if int(mask.sum()) > 0:
+            ce = orc.fisher_ce(A128[mask], strong[mask])
+            (ce.mean() * mask.float().mean()).backward()
+
+    def c3():
+        leaf = A3.clone().requires_grad_(True)
+        losses, _ = orc.laplace_nll("RLaplace", leaf, R3, grid.reshape(-1, 3, 3))
+        losses.mean().backward()
+
+    out = {"kind": "port", "cores": cores, "host_cpus": os.cpu_count()}
+    out["c1_fisher_b32_fwd_bwd_us"] = 1e6 * best(c1, 5)
+    out["c2_teacher_step_32_128_us"] = 1e6 * best(c2_teacher, 3)
+    out["c2_ssl_step_ce_32_128_us"] = 1e6 * best(c2_ssl, 3)
+    t = best(c3, 2)
+    out["c3_laplace_rot_per_s"] = A3.shape[0] / t
+    out["c3_sample"] = f"{A3.shape[0]} rotations x {grid.shape[0]} grid points fwd+bwd, {t:.2f} s, rate extrapolates linearly"
+    t = best(lambda: orc.geodesic_deg(Rp.reshape(-1, 3, 3), Rg.reshape(-1, 3, 3)), 2)
+    geo_rate = Rp.shape[0] / t
+    m = ge.shape[0]
+    t2 = best(lambda: orc.err_deg_from_matrices(Rp[:m].reshape(-1, 3, 3), Rg[:m].reshape(-1, 3, 3), ge), 1)
+    euler_rate = m / t2
+    out["c4_geodesic_pairs_per_s"] = geo_rate
+    out["c4_euler_mae_pairs_per_s"] = euler_rate
+    out["c4_metrics_pairs_per_s"] = 1.0 / (1.0 / geo_rate + 1.0 / euler_rate)     # both metrics per pair, as K4 computes
+    out["c4_sample"] = f"geodesic on {Rp.shape[0]} pairs ({t:.2f} s), Euler MAE on {m} pairs ({t2:.2f} s)"
     return out
 
 

@@ -6,7 +6,10 @@
  * Every function returns 0 on success, -(cudaError_t) for a CUDA failure and
  * SUHPE_EINVAL for a bad argument; nothing throws and nothing synchronises the
  * device except the `_host` pipeline and suhpe_select_read.  `stream` is a
- * cudaStream_t passed as void* (NULL = legacy default stream).
+ * cudaStream_t passed as void* (NULL = legacy default stream).  The library keeps
+ * no mutable process-wide settings: everything a call depends on is an argument
+ * (or lives in a handle the caller created), so calls from several threads,
+ * streams and devices do not interact.
  *
  * The reference (hnuzhy/SemiUHPE) has no FFI: the path sits behind plain Python
  * functions.  Each entry point names the reference function(s) it replaces
@@ -24,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SUHPE_ABI_VERSION 1
+#define SUHPE_ABI_VERSION 2
 #define SUHPE_EINVAL (-100000)
 
 /* bits OR-ed into the optional device `status` word */
@@ -52,21 +55,22 @@ int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U
  *   Rout    = U V^T                                        batch_torch_A_to_R fisher_utils.py:39-48
  *   entropy = log f(S) + sum_j S_j (1 - g_j)               fisher_entropy fisher_utils.py:70-81
  *   logC, S (n,3), G = dlogC/dS (n,3)                      logC_F torch_norm_factor.py:66-92
- *   hist   += histogram of the top 11 bits of the entropy keys (first radix-select pass, chained on
- *             the same stream while the entropies are L2-resident; needs `entropy` non-NULL)
- * Rgt may be NULL (then nll = overreg*logC and grad has no -Rgt term); every output is nullable. */
-int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg,
+ *   hist   += histogram of the top 11 bits of the entropy keys: the first radix-select pass, counted
+ *             inside the kernel as each entropy is produced (warp-aggregated atomic adds into the 2048
+ *             counters; `entropy` itself may be NULL)
+ * Rgt may be NULL (then nll = overreg*logC and grad has no -Rgt term); every output is nullable.
+ *
+ * cut_bits -- negligible-node cut of the quadrature.  Every integrand of
+ * src/fisher/torch_norm_factor.py:33-63 decays like exp(-c(1-x)) away from x = 1, so a prefix of the 512
+ * nodes contributes less than 2^-cut_bits of the normaliser sum in total; K2 skips that prefix where a
+ * per-sample bound PROVES it (rigorous upper bound of the prefix mass against a rigorous lower bound of
+ * the sum: cut_threshold / cut_index in csrc/so3_math.cuh, float64 check in tests/test_emul_math.py).
+ * SUHPE_CUT_BITS_DEFAULT = 26 is an eighth of an fp32 ulp of the sum (below what the reference's own fp32
+ * torch.sum resolves); 0 evaluates all 512 nodes of every integral. */
+#define SUHPE_CUT_BITS_DEFAULT 26
+int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg, int32_t cut_bits,
                            float* nll, float* grad, float* Rout, float* entropy, float* logC,
                            float* S, float* G, uint64_t* hist, int* status, void* stream);
-
-/* Negligible-node cut of the K2 quadrature (process-wide setting; returns the previous value).
- * Every integrand of src/fisher/torch_norm_factor.py:33-63 decays like exp(-c(1-x)) away from
- * x = 1, so a prefix of the 512 nodes contributes less than 2^-bits of the normaliser sum in total;
- * K2 skips that prefix where a per-sample bound PROVES it (rigorous upper bound of the prefix mass
- * against a rigorous lower bound of the sum: cut_threshold / cut_index in csrc/so3_math.cuh, float64
- * check in tests/test_emul_math.py).  Default 26 (an eighth of an fp32 ulp of the sum: below what
- * the reference's own fp32 torch.sum resolves); 0 evaluates all 512 nodes of every integral. */
-int suhpe_set_quadrature_cut_bits(int bits);
 
 /* fisher_CE(A1 = target, A2 = prediction) -> ce (n) and d ce_i / d A2_i (n,9, nullable): the
  * cross entropy of two matrix-Fisher densities through their Bingham forms, the reference's default
@@ -75,16 +79,28 @@ int suhpe_set_quadrature_cut_bits(int bits);
  * launches (the quadratures of A1 and A2) and one closing kernel that evaluates the value and
  * the gradient in closed form (what autograd yields through torch.svd, matrix_to_quaternion and
  * the logC_F backward).  A1 is a constant (the agent detaches the teacher: src/agent.py:107).
+ * keep (n, nullable): rows with keep[i] == 0 are the ones the reference's boolean gather drops before
+ * the loss (src/agent.py:152-160); they get ce = 0 and a zero gradient and raise no status bit, whatever
+ * their inputs hold.
  * workspace: SUHPE_FISHER_CE_WORKSPACE_FLOATS * n floats of device scratch, caller-owned. */
 #define SUHPE_FISHER_CE_WORKSPACE_FLOATS 10
-int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
-                        float* workspace, int* status, void* stream);
+int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, int32_t cut_bits, const uint8_t* keep,
+                        float* ce, float* gradA2, float* workspace, int* status, void* stream);
 /* Same, with G1 = d logC / dS of the target (n,3) supplied by the caller: the training step has
  * it already -- the entropy launch on the teacher output (suhpe_fisher_fused_f32 with G) produced
  * it, and the rotate-augmentation adjustment (a rotation applied on one side) leaves the singular
  * values, hence G1, unchanged -- so the cross entropy costs one quadrature instead of two. */
-int suhpe_fisher_ce_with_g1_f32(const float* A1, const float* G1, const float* A2, int64_t n, float* ce,
-                                float* gradA2, float* workspace, int* status, void* stream);
+int suhpe_fisher_ce_with_g1_f32(const float* A1, const float* G1, const float* A2, int64_t n, int32_t cut_bits,
+                                const uint8_t* keep, float* ce, float* gradA2, float* workspace, int* status,
+                                void* stream);
+
+/* out[i, :] = w_i * in[i, :] for rows of `width` floats; w_i = row_weight[i] (n, nullable) times
+ * *scalar_weight (device scalar, nullable).  The backward of the loss mirrors: the per-sample gradient
+ * the forward launch produced times the incoming d L / d loss_i, without leaving the stream.
+ * keep (n, nullable): rows with keep[i] == 0 are written as zeros regardless of `in` (0 * NaN never forms).
+ * in == out is allowed. */
+int suhpe_scale_rows_f32(const float* in, int64_t n, int32_t width, const float* row_weight,
+                         const float* scalar_weight, const uint8_t* keep, float* out, void* stream);
 
 /* Rotate-augmentation adjustment of the teacher's parameter matrices before they become pseudo
  * labels (src/agent.py:110-119): mode 0 (train_labeled "DAD3DHeads") out = aug_rot * pred;
@@ -104,7 +120,7 @@ int suhpe_ema_update_f32(float* const* ema, const float* const* src, const int64
 /* K2 on given singular values: logC_F(S) and its backward G = dlogC/dS, entropy(S)
  * (src/fisher/torch_norm_factor.py:66-92 `logC_F`; S (n,3) sorted s1>=s2>=|s3| like every
  * reference call site).  Outputs nullable. */
-int suhpe_fisher_from_s_f32(const float* S, int64_t n, float* logC, float* G, float* entropy,
+int suhpe_fisher_from_s_f32(const float* S, int64_t n, int32_t cut_bits, float* logC, float* G, float* entropy,
                             int* status, void* stream);
 
 /* K2L -- rotation-Laplace NLL forward+backward against an SO(3) grid (N,9), device resident.
@@ -152,17 +168,6 @@ int suhpe_so3_metrics_f32(const float* Rp, const float* Rg, const float* gt_eule
                           int32_t full_range, float* geo_deg, float* frob, float* euler,
                           float* abs_err, float* mae, double* sums, int* status, void* stream);
 
-/* FP32-pipe probe used by bench.py for the roofline denominator: launches `blocks` CTAs of
- * 256 threads, each thread running `iters` rounds of 8 independent dependent-FMA chains.
- * variant 0: scalar FFMA, 1: packed fma.rn.f32x2, 2: FFMA + 1 MUFU.EX2 per 8 FMA,
- * 3: packed and scalar chains interleaved 1:1, 4 / 5: every packed FMA followed by one LOP3 / IADD
- * (does a 2-cycle FFMA2 leave an issue slot for the ALU pipe?).
- * 6 / 7: packed FMA with an immediate addend / a broadcast scalar multiplier (K2's Horner operand forms).
- * FMAs executed = blocks*256*iters*64*{1, 2, 1, 3, 2, 2, 2, 2}[variant].
- * variant 100+v: K2 pass-body probe, 16 warps per CTA each running `iters` 128-node passes of run type
- * v&3 (bit 2: no table loads, bit 3: no MUFU, bit 4: no slot mask); 46 packed FMA-pipe ops per pass. */
-int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks, void* stream);
-
 /* Host-buffer pipeline (what bench.py's e2e leg and a non-torch host would call):
  * the teacher-side filter step over a pool of n (A,Rgt) pairs living in HOST memory
  * (pinned for full PCIe rate).  Chunks move through three in-order queues -- host->device
@@ -170,9 +175,10 @@ int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks
  * buffers, so both copy engines and the SMs are busy at once; then K3 selects the k-th
  * smallest entropy of the whole pool and the mask is emitted and copied back.
  * Replaces the per-batch loop of src/agent.py:357-417 (teacher forward -> fisher_entropy ->
- * host sort).  Host outputs nullable; threshold/kept written on return (the call blocks). */
+ * host sort).  Host outputs nullable; threshold/kept written on return (the call blocks).
+ * `cut_bits` (see suhpe_fisher_fused_f32) is fixed per pipeline at creation. */
 typedef struct suhpe_pipeline suhpe_pipeline;
-int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk);
+int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk, int32_t cut_bits);
 int suhpe_pipeline_destroy(suhpe_pipeline* p);
 int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
                              float overreg, uint64_t k, float* nll_host, float* grad_host,
@@ -183,11 +189,44 @@ int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float
  * status_dev (all caller-owned device memory).  Returns once everything is queued; `stream`
  * is made to wait for the last kernel, so the caller queues the global select on it (K3 passes
  * + an all-gather of the histograms, semiuhpe_b200/distributed.py) while the device->host copies
- * drain.  suhpe_pipeline_sync blocks until the host buffers are complete. */
+ * drain.  suhpe_pipeline_sync blocks until the host buffers are complete.  Calls on one pipeline
+ * may follow each other without a sync in between: a chunk buffer is reused only after the kernel
+ * and the device->host copies of its previous use -- in this or an earlier call -- have finished
+ * (the HOST output arrays of the earlier call must of course not be reused before a sync). */
 int suhpe_fisher_pool_host(suhpe_pipeline* p, const float* A_host, const float* Rgt_host, int64_t n,
                            float overreg, float* nll_host, float* grad_host, float* entropy_host,
                            float* ent_dev, uint64_t* hist_dev, int* status_dev, void* stream);
 int suhpe_pipeline_sync(suhpe_pipeline* p);
+
+/* The loss head of one semi-supervised training step (SSLAgent.forward + the backward of
+ * train_func, src/agent.py:76-83,99-166,194-210) in ONE call: a fixed sequence of launches over
+ * three forked streams, no host synchronisation, no dynamic shapes -- CUDA-graph capturable.
+ *   labeled     out_l (b_l,9) student output, gt_l (b_l,9) rotations:
+ *               losses_l = KL_Fisher(out_l, gt_l, overreg), Rest_l = batch_torch_A_to_R(out_l)      :76-83
+ *   unlabeled   pred_weak (b_u,9) teacher output (a constant), pred_strong (b_u,9) student output:
+ *               entropy = fisher_entropy(pred_weak), mask = entropy < conf_thres                    :139,148
+ *               adjusted = rotate-augmentation adjustment of pred_weak (aug_rot nullable)           :110-122
+ *               unsup_kind 0 ('ce'):  l_u = fisher_CE(adjusted, pred_strong)                        :155
+ *               unsup_kind 1 ('nll'): l_u = KL_Fisher(pred_strong, batch_torch_A_to_R(adjusted))    :157
+ *   losses[0] = mean(losses_l)                       losses[1] = sum(mask ? l_u : 0) / b_u   (:163,166)
+ *   losses[2] = mask ratio                           losses[3] = losses[0] + ssl_lambda * losses[1] (:203)
+ *   grad_l      = d losses[3] / d out_l        (b_l,9)
+ *   grad_strong = d losses[3] / d pred_strong  (b_u,9), exactly zero for filtered rows
+ * conf_thres is read from conf_thres_dev if non-NULL (e.g. suhpe_select_threshold_ptr) else conf_thres_host.
+ * Optional outputs (nullable): Rest_l (b_l,9), entropy (b_u), mask (b_u), pseudo (b_u,9) = the projected
+ * pseudo labels of every row, losses_l (b_l), losses_u (b_u, zero for filtered rows).
+ * b_u may be 0 (supervised step, train_func_s1: src/agent.py:253-270); then only the labeled part runs.
+ * The handle owns the forked streams, their events and the device scratch; one call at a time per handle. */
+typedef struct suhpe_ssl_step suhpe_ssl_step;
+int suhpe_ssl_step_create(suhpe_ssl_step** out, int64_t max_labeled, int64_t max_unlabeled);
+int suhpe_ssl_step_destroy(suhpe_ssl_step* ctx);
+int suhpe_ssl_step_f32(suhpe_ssl_step* ctx, const float* out_l, const float* gt_l, int64_t b_l,
+                       const float* pred_weak, const float* pred_strong, int64_t b_u,
+                       const float* aug_rot, int32_t aug_mode, const float* conf_thres_dev, float conf_thres_host,
+                       float overreg, float ssl_lambda, int32_t unsup_kind, int32_t cut_bits,
+                       float* losses, float* grad_l, float* grad_strong,
+                       float* Rest_l, float* entropy, uint8_t* mask, float* pseudo, float* losses_l, float* losses_u,
+                       int* status, void* stream);
 
 #ifdef __cplusplus
 }

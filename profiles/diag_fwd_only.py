@@ -1,0 +1,18 @@
+"""Diagnostic: is the forward-only launch (NFAM=1) bit-identical to the full launch (NFAM=3)?"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from semiuhpe_b200 import _ops
+dev = torch.device("cuda:0")
+gen = torch.Generator().manual_seed(2024)
+scales = torch.tensor([0.3, 1.0, 3.0, 5.0, 10.0, 20.0]).repeat_interleave(1000)
+A = (torch.randn(len(scales), 9, generator=gen) * scales[:, None]).to(dev)
+for n in (6000, 200000):
+    a = A if n == 6000 else (10 * torch.randn(n, 9, generator=gen)).to(dev)
+    full = _ops.fisher_fused(a, None, 1.0, nll=True, entropy=True)["nll"]
+    fwd = _ops.fisher_fused(a, None, 1.0, nll=True)["nll"]
+    full2 = _ops.fisher_fused(a, None, 1.0, nll=True, entropy=True)["nll"]
+    d = (full - fwd).abs()
+    bad = (full != fwd)
+    print(f"n={n}: full-vs-fwd mismatches {int(bad.sum())} max|d|={d.max().item():.3e} rel={(d / full.abs().clamp(min=1e-3)).max().item():.3e}; "
+          f"full rerun identical: {bool(torch.equal(full, full2))}; first bad idx {bad.nonzero().flatten()[:8].tolist()}")

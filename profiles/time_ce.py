@@ -16,7 +16,7 @@ ce, grad = torch.empty(n, device=dev), torch.empty(n, 9, device=dev)
 work = torch.empty(_capi.FISHER_CE_WORKSPACE_FLOATS * n, device=dev)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 P, lib = _capi.ptr, _capi.lib()
-call = lambda: _capi.check(lib.suhpe_fisher_ce_f32(P(A1), P(A2), n, P(ce), P(grad), P(work), P(status), _capi.stream()), "ce")
+call = lambda: _capi.check(lib.suhpe_fisher_ce_f32(P(A1), P(A2), n, 26, None, P(ce), P(grad), P(work), P(status), _capi.stream()), "ce")
 for _ in range(2):
     call()
 torch.cuda.synchronize()

@@ -15,10 +15,11 @@ R = _quat_to_matrix(torch.nn.functional.normalize(torch.randn(n, 4, device=dev, 
 nll, grad, ent = torch.empty(n, device=dev), torch.empty(n, 9, device=dev), torch.empty(n, device=dev)
 hist = torch.zeros(2048, dtype=torch.int64, device=dev)
 lib, P, S = _capi.lib(), _capi.ptr, _capi.stream
+BITS = [26]
 def run():
-    _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, 1.025, P(nll), P(grad), None, P(ent), None, None, None, P(hist), None, S()), "f")
+    _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, 1.025, BITS[0], P(nll), P(grad), None, P(ent), None, None, None, P(hist), None, S()), "f")
 for bits in [int(b) for b in os.environ.get("BITS", "0,26").split(",")]:
-    semiuhpe_b200.set_quadrature_cut_bits(bits)
+    BITS[0] = bits
     for _ in range(3): run()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -28,9 +29,9 @@ for bits in [int(b) for b in os.environ.get("BITS", "0,26").split(",")]:
     ms = a.elapsed_time(b) / 10
     print(f"cut_bits={bits:2d}  {ms:8.3f} ms  {n/ms/1e3:9.1f} Mrot/s  {n*69120/ms/1e9:6.2f} TFLOP/s(alg)  nll.mean={nll.mean().item():.6f} ent.mean={ent.mean().item():.6f}")
 # forward-only NLL (no gradient, no entropy): the normaliser family alone
-semiuhpe_b200.set_quadrature_cut_bits(26)
+BITS[0] = 26
 def run_fwd():
-    _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, 1.025, P(nll), None, None, None, None, None, None, None, None, S()), "f")
+    _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, 1.025, 26, P(nll), None, None, None, None, None, None, None, None, S()), "f")
 for _ in range(3): run_fwd()
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

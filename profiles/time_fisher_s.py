@@ -8,13 +8,12 @@ from semiuhpe_b200 import _capi
 n = 1 << 22
 dev = torch.device("cuda:0")
 lib, P, S = _capi.lib(), _capi.ptr, _capi.stream
-semiuhpe_b200.set_quadrature_cut_bits(0)
 out = torch.empty(n, device=dev); G = torch.empty(n, 3, device=dev)
 cases = {"all-LL (1000,600,300)": (1000., 600., 300.), "all-SS (1.5,1,0.5)": (1.5, 1.0, 0.5), "generic (25,13,6)": (25., 13., 6.),
          "generic (25,13,-6)": (25., 13., -6.), "kappa 40 (40,40,40)": (40., 40., 40.)}
 for name, sv in cases.items():
     Sv = torch.tensor(sv, device=dev).repeat(n, 1).contiguous()
-    f = lambda: _capi.check(lib.suhpe_fisher_from_s_f32(P(Sv), n, P(out), P(G), None, None, S()), "s")
+    f = lambda: _capi.check(lib.suhpe_fisher_from_s_f32(P(Sv), n, 0, P(out), P(G), None, None, S()), "s")
     for _ in range(3): f()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

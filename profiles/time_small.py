@@ -15,7 +15,7 @@ for n in (32, 128, 1024, 8192):
     A = 10 * torch.randn(n, 9, device=dev, generator=gen)
     R = _quat_to_matrix(torch.nn.functional.normalize(torch.randn(n, 4, device=dev, generator=gen), dim=1)).reshape(n, 9).contiguous()
     nll, grad, ent = torch.empty(n, device=dev), torch.empty(n, 9, device=dev), torch.empty(n, device=dev)
-    run = lambda: _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, 1.025, P(nll), P(grad), None, P(ent), None, None, None, None, None, S()), "f")
+    run = lambda: _capi.check(lib.suhpe_fisher_fused_f32(P(A), P(R), n, 1.025, 26, P(nll), P(grad), None, P(ent), None, None, None, None, None, S()), "f")
     for _ in range(10): run()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -22,9 +22,10 @@ library must have been built (``__graft_entry__.build()``).
 """
 from . import _capi
 
-__all__ = ["set_error_checking", "error_checking", "library_path", "set_quadrature_cut_bits"]
+__all__ = ["set_error_checking", "error_checking", "library_path", "set_quadrature_cut_bits", "quadrature_cut_bits"]
 
 _CHECK = True
+_CUT_BITS = _capi.CUT_BITS_DEFAULT
 
 
 def set_error_checking(enabled):
@@ -32,9 +33,15 @@ def set_error_checking(enabled):
     on out-of-range traces (pytorch3d ``ValueError``).  Reproducing that needs one
     4-byte device->host read per call (a sync the reference pays anyway at every
     ``.cpu()``).  Disable for sync-free / CUDA-graph use; the kernels then only
-    leave NaNs in the outputs of the offending rows."""
+    leave NaNs in the outputs of the offending rows.  Switching it back on clears
+    whatever the unchecked launches left in the status words, so a later call is
+    never blamed for an earlier one."""
     global _CHECK
-    _CHECK = bool(enabled)
+    enabled = bool(enabled)
+    if enabled and not _CHECK:
+        from . import _ops
+        _ops.reset_status()
+    _CHECK = enabled
 
 
 def error_checking():
@@ -42,10 +49,20 @@ def error_checking():
 
 
 def set_quadrature_cut_bits(bits):
-    """Negligible-node cut of the Fisher quadrature (``suhpe_set_quadrature_cut_bits``): nodes
-    whose total contribution is provably below ``2**-bits`` of the normaliser sum are skipped.
-    Default 26; ``0`` evaluates all 512 nodes of every integral.  Returns the previous value."""
-    return _capi.lib().suhpe_set_quadrature_cut_bits(int(bits))
+    """Default ``cut_bits`` the Python mirrors pass to the C ABI (the library itself keeps no setting: it is a
+    per-call argument of ``suhpe_fisher_fused_f32``).  Nodes whose total contribution is provably below
+    ``2**-bits`` of the normaliser sum are skipped; default 26; ``0`` evaluates all 512 nodes of every
+    integral.  Returns the previous value."""
+    global _CUT_BITS
+    bits = int(bits)
+    if bits > 60:
+        raise ValueError("cut_bits must be <= 60")
+    prev, _CUT_BITS = _CUT_BITS, max(bits, 0)
+    return prev
+
+
+def quadrature_cut_bits():
+    return _CUT_BITS
 
 
 def library_path():

@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsemiuhpe_b200.so")
-SOURCES = ["fisher_kernels.cu", "laplace_kernels.cu", "select_kernels.cu", "metrics_kernels.cu", "ema_kernels.cu", "capi.cu"]
+SOURCES = ["fisher_kernels.cu", "laplace_kernels.cu", "select_kernels.cu", "metrics_kernels.cu", "ema_kernels.cu",
+           "ssl_kernels.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -10,17 +10,27 @@ import torch
 
 import semiuhpe_b200 as _pkg
 from . import _capi
-from ._capi import as_records, check, lib, ptr, stream
+from ._capi import as_records, check, lib, on_device, ptr, stream
 
 _STATUS = {}
 
 
 def _status_word(device):
-    t = _STATUS.get(device)
+    """One status word per (device, stream): a bit set by a launch on one stream is never reported against
+    an op running on another."""
+    key = (device.index, stream(device.index))
+    t = _STATUS.get(key)
     if t is None:
         t = torch.zeros(1, dtype=torch.int32, device=device)
-        _STATUS[device] = t
+        _STATUS[key] = t
     return t
+
+
+def reset_status():
+    """Clear every status word (called when error checking is switched back on: bits raised while it was
+    off -- graph replays, sync-free steps -- must not be blamed on the next unrelated call)."""
+    for t in _STATUS.values():
+        t.zero_()
 
 
 def _raise_from_status(status, what):
@@ -40,8 +50,24 @@ def _raise_from_status(status, what):
             raise AssertionError(f"{what}: the cross entropy is NaN or Inf (the reference asserts: fisher_utils.py:98)")
 
 
+def _cut(cut_bits):
+    return _pkg.quadrature_cut_bits() if cut_bits is None else int(cut_bits)
+
+
+def _keep_vector(keep, n, name="keep"):
+    """(n,) bool / uint8 CUDA tensor -> contiguous uint8 view (None passes through)."""
+    if keep is None:
+        return None
+    if not keep.is_cuda or keep.numel() != n or keep.dtype not in (torch.bool, torch.uint8):
+        raise RuntimeError(f"{name} must be a CUDA bool/uint8 tensor with {n} elements")
+    k = keep.reshape(-1)
+    if not k.is_contiguous():
+        k = k.contiguous()
+    return k.view(torch.uint8) if k.dtype == torch.bool else k
+
+
 def fisher_fused(A, R=None, overreg=1.0, *, nll=False, grad=False, rot=False, entropy=False,
-                 logC=False, S=False, G=False, hist=None, what="fisher"):
+                 logC=False, S=False, G=False, hist=None, what="fisher", cut_bits=None):
     """K2.  Returns a dict of the requested outputs (keys = argument names)."""
     A9 = as_records(A, "A")
     n = A9.shape[0]
@@ -62,19 +88,20 @@ def fisher_fused(A, R=None, overreg=1.0, *, nll=False, grad=False, rot=False, en
     if G: out["G"] = new(n, 3)
     if n == 0:
         return out
-    status = _status_word(dev)
-    with torch.cuda.device(dev):
+    with on_device(dev) as idx:
+        status = _status_word(dev)
         check(lib().suhpe_fisher_fused_f32(
-            ptr(A9), ptr(R9), n, float(overreg), ptr(out.get("nll")), ptr(out.get("grad")),
+            ptr(A9), ptr(R9), n, float(overreg), _cut(cut_bits), ptr(out.get("nll")), ptr(out.get("grad")),
             ptr(out.get("rot")), ptr(out.get("entropy")), ptr(out.get("logC")), ptr(out.get("S")),
-            ptr(out.get("G")), ptr(hist), ptr(status), stream()), what)
+            ptr(out.get("G")), ptr(hist), ptr(status), stream(idx)), what)
     _raise_from_status(status, what)
     return out
 
 
-def fisher_ce(A1, A2, *, grad=False, target_G=None):
+def fisher_ce(A1, A2, *, grad=False, target_G=None, keep=None, cut_bits=None):
     """fisher_CE value (n,) and, on request, d ce_i / d A2_i (n,9): two K2 launches + the closing kernel
-    (one K2 launch when ``target_G`` = d logC/dS of the target (n,3) is supplied)."""
+    (one K2 launch when ``target_G`` = d logC/dS of the target (n,3) is supplied).  ``keep`` (n, bool):
+    rows the caller's mask filtered out -- they get ce = 0, a zero gradient and raise nothing."""
     T9, P9 = as_records(A1, "A1"), as_records(A2, "A2")
     n = P9.shape[0]
     if T9.shape[0] != n:
@@ -84,19 +111,50 @@ def fisher_ce(A1, A2, *, grad=False, target_G=None):
     if grad: out["grad"] = torch.empty((n, 9), dtype=torch.float32, device=dev)
     if n == 0:
         return out
+    K = _keep_vector(keep, n)
     work = torch.empty(_capi.FISHER_CE_WORKSPACE_FLOATS * n, dtype=torch.float32, device=dev)
-    status = _status_word(dev)
-    with torch.cuda.device(dev):
+    with on_device(dev) as idx:
+        status = _status_word(dev)
         if target_G is None:
-            check(lib().suhpe_fisher_ce_f32(ptr(T9), ptr(P9), n, ptr(out["ce"]), ptr(out.get("grad")), ptr(work),
-                                            ptr(status), stream()), "fisher_CE")
+            check(lib().suhpe_fisher_ce_f32(ptr(T9), ptr(P9), n, _cut(cut_bits), ptr(K), ptr(out["ce"]), ptr(out.get("grad")),
+                                            ptr(work), ptr(status), stream(idx)), "fisher_CE")
         else:
             G3 = as_records(target_G, "target_G", 3)
             if G3.shape[0] != n:
                 raise RuntimeError(f"shape mismatch: target_G has {G3.shape[0]} rows, A2 has {n}")
-            check(lib().suhpe_fisher_ce_with_g1_f32(ptr(T9), ptr(G3), ptr(P9), n, ptr(out["ce"]), ptr(out.get("grad")),
-                                                    ptr(work), ptr(status), stream()), "fisher_CE")
+            check(lib().suhpe_fisher_ce_with_g1_f32(ptr(T9), ptr(G3), ptr(P9), n, _cut(cut_bits), ptr(K), ptr(out["ce"]),
+                                                    ptr(out.get("grad")), ptr(work), ptr(status), stream(idx)), "fisher_CE")
     _raise_from_status(status, "fisher_CE")
+    return out
+
+
+def scale_rows(rows, row_weight=None, scalar_weight=None, keep=None):
+    """``rows * row_weight[:, None] * scalar_weight`` with filtered rows (``keep`` false) written as exact zeros:
+    the backward of the loss mirrors (per-sample gradient x incoming gradient) as one launch."""
+    if not rows.is_cuda or rows.dtype != torch.float32:
+        raise RuntimeError("scale_rows: rows must be a CUDA float32 tensor")
+    r = rows if rows.is_contiguous() else rows.contiguous()
+    n = r.shape[0] if r.dim() > 1 else r.numel()
+    width = r.numel() // max(n, 1) if n else 1
+    out = torch.empty_like(r)
+    if n == 0:
+        return out
+    w = None
+    if row_weight is not None:
+        w = row_weight.detach().reshape(-1)
+        if w.numel() == 1:
+            scalar_weight, w = (w if scalar_weight is None else scalar_weight * w), None
+        else:
+            if w.numel() != n:
+                raise RuntimeError(f"scale_rows: {w.numel()} weights for {n} rows")
+            w = w.to(torch.float32)
+            w = w if w.is_contiguous() else w.contiguous()
+    sw = None
+    if scalar_weight is not None:
+        sw = scalar_weight.detach().reshape(-1).to(torch.float32)
+    K = _keep_vector(keep, n)
+    with on_device(r.device) as idx:
+        check(lib().suhpe_scale_rows_f32(ptr(r), n, width, ptr(w), ptr(sw), ptr(K), ptr(out), stream(idx)), "scale_rows")
     return out
 
 
@@ -108,8 +166,8 @@ def rotate_adjust(pred, aug_rot, mode):
         raise RuntimeError(f"shape mismatch: pred_weak has {n} matrices, aug_rot_mat has {R9.shape[0]}")
     out = torch.empty((n, 9), dtype=torch.float32, device=P9.device)
     if n:
-        with torch.cuda.device(P9.device):
-            check(lib().suhpe_rotate_adjust_f32(ptr(P9), ptr(R9), n, int(mode), ptr(out), stream()), "rotate_adjust")
+        with on_device(P9.device) as idx:
+            check(lib().suhpe_rotate_adjust_f32(ptr(P9), ptr(R9), n, int(mode), ptr(out), stream(idx)), "rotate_adjust")
     return out
 
 
@@ -139,11 +197,11 @@ def ema_update(ema_tensors, src_tensors, alpha, mode):
     n_arr = NumArr(*[e.numel() for e in ema_tensors])
     a32 = ctypes.c_float(float(alpha)).value
     oma32 = ctypes.c_float(1.0 - float(alpha)).value
-    with torch.cuda.device(dev):
-        check(lib().suhpe_ema_update_f32(e_arr, s_arr, n_arr, count, a32, oma32, int(mode), stream()), "ema_update")
+    with on_device(dev) as idx:
+        check(lib().suhpe_ema_update_f32(e_arr, s_arr, n_arr, count, a32, oma32, int(mode), stream(idx)), "ema_update")
 
 
-def fisher_from_s(S, *, logC=True, G=False, entropy=False):
+def fisher_from_s(S, *, logC=True, G=False, entropy=False, cut_bits=None):
     """K2 on given singular values (logC_F)."""
     S3 = as_records(S, "S", 3)
     n = S3.shape[0]
@@ -153,9 +211,9 @@ def fisher_from_s(S, *, logC=True, G=False, entropy=False):
     if G: out["G"] = torch.empty((n, 3), dtype=torch.float32, device=dev)
     if entropy: out["entropy"] = torch.empty(n, dtype=torch.float32, device=dev)
     if n:
-        with torch.cuda.device(dev):
-            check(lib().suhpe_fisher_from_s_f32(ptr(S3), n, ptr(out.get("logC")), ptr(out.get("G")),
-                                                ptr(out.get("entropy")), None, stream()), "logC_F")
+        with on_device(dev) as idx:
+            check(lib().suhpe_fisher_from_s_f32(ptr(S3), n, _cut(cut_bits), ptr(out.get("logC")), ptr(out.get("G")),
+                                                ptr(out.get("entropy")), None, stream(idx)), "logC_F")
     return out
 
 
@@ -173,9 +231,9 @@ def proper_svd(A, *, rot=True, S=False, U=False, V=False, what="svd"):
     if n == 0:
         return out
     status = _status_word(dev)
-    with torch.cuda.device(dev):
+    with on_device(dev) as idx:
         check(lib().suhpe_proper_svd_f32(ptr(A9), n, ptr(out.get("rot")), ptr(out.get("S")),
-                                         ptr(out.get("U")), ptr(out.get("V")), ptr(status), stream()), what)
+                                         ptr(out.get("U")), ptr(out.get("V")), ptr(status), stream(idx)), what)
     _raise_from_status(status, what)
     return out
 
@@ -197,9 +255,9 @@ def laplace_nll(A, R, grids, *, grad=False, mode=True, logF=False):
     if n == 0:
         return out
     status = _status_word(dev)
-    with torch.cuda.device(dev):
+    with on_device(dev) as idx:
         check(lib().suhpe_laplace_nll_f32(ptr(A9), ptr(R9), n, ptr(g9), N, ptr(out["nll"]), ptr(out.get("grad")),
-                                          ptr(out.get("mode")), ptr(out.get("logF")), ptr(status), stream()),
+                                          ptr(out.get("mode")), ptr(out.get("logF")), ptr(status), stream(idx)),
               "laplace_nll")
     _raise_from_status(status, "laplace_nll")
     return out
@@ -227,12 +285,12 @@ def so3_metrics(Rp, Rg=None, gt_euler=None, *, full_range=False, geo=False, frob
     if n == 0:
         return out
     status = _status_word(dev)
-    with torch.cuda.device(dev):
+    with on_device(dev) as idx:
         mode = 2 if full_range == "dad" else int(bool(full_range))
         check(lib().suhpe_so3_metrics_f32(ptr(P9), ptr(G9), ptr(E3), n, mode,
                                           ptr(out.get("geo")), ptr(out.get("frob")), ptr(out.get("euler")),
                                           ptr(out.get("abs_err")), ptr(out.get("mae")), ptr(out.get("sums")),
-                                          ptr(status), stream()), "so3_metrics")
+                                          ptr(status), stream(idx)), "so3_metrics")
     if geo or sums:
         _raise_from_status(status, "so3_relative_angle")
     return out
@@ -251,9 +309,9 @@ class SelectWorkspace:
 
     def read(self):
         thr, key, kept = ctypes.c_float(), ctypes.c_uint32(), ctypes.c_uint64()
-        with torch.cuda.device(self.device):
+        with on_device(self.device) as idx:
             check(lib().suhpe_select_read(ptr(self.state), ctypes.byref(thr), ctypes.byref(key),
-                                          ctypes.byref(kept), stream()), "select_read")
+                                          ctypes.byref(kept), stream(idx)), "select_read")
         return thr.value, key.value, kept.value
 
 
@@ -273,9 +331,9 @@ def entropy_threshold_device(entropy, k, ws=None, first_pass_hist=None):
     if not 0 <= k < n:
         raise IndexError(f"index {k} is out of bounds for axis 0 with size {n}")
     ws = ws or SelectWorkspace(e.device)
-    with torch.cuda.device(e.device):
+    with on_device(e.device) as idx:
         check(lib().suhpe_entropy_threshold_f32(ptr(e), n, k, ptr(ws.state), ptr(ws.hist[1]),
-                                                ptr(first_pass_hist), stream()), "entropy_threshold")
+                                                ptr(first_pass_hist), stream(idx)), "entropy_threshold")
     return ws
 
 
@@ -287,11 +345,96 @@ def entropy_mask(entropy, thr, ws=None, want_mask=True):
     mask = torch.empty(n, dtype=torch.bool, device=e.device) if want_mask else None
     kept = torch.zeros(1, dtype=torch.int64, device=e.device)
     if n:
-        with torch.cuda.device(e.device):
+        with on_device(e.device) as idx:
             if isinstance(thr, SelectWorkspace):
                 check(lib().suhpe_entropy_mask_f32(ptr(e), n, thr.threshold_ptr(), 0.0, ptr(mask), ptr(kept),
-                                                   stream()), "entropy_mask")
+                                                   stream(idx)), "entropy_mask")
             else:
                 check(lib().suhpe_entropy_mask_f32(ptr(e), n, None, float(thr), ptr(mask), ptr(kept),
-                                                   stream()), "entropy_mask")
+                                                   stream(idx)), "entropy_mask")
     return mask, kept
+
+
+class SslStep:
+    """Handle of ``suhpe_ssl_step_f32``: the loss head of a whole semi-supervised step -- supervised Fisher NLL,
+    teacher entropy, mask, rotate-augmentation adjustment, fisher_CE (or NLL) against the pseudo labels, the
+    means, ``loss_all`` and its gradients -- as one C call (a fixed launch sequence over three forked streams)."""
+
+    def __init__(self, max_labeled, max_unlabeled, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SslStep needs a CUDA device: semiuhpe_b200 has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_l, self.max_u = int(max_labeled), int(max_unlabeled)
+        self._h = ctypes.c_void_p()
+        with on_device(self.device):
+            check(lib().suhpe_ssl_step_create(ctypes.byref(self._h), self.max_l, self.max_u), "ssl_step_create")
+
+    def close(self):
+        if self._h:
+            lib().suhpe_ssl_step_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, out_l, gt_l, pred_weak=None, pred_strong=None, conf_thres=0.0, *, aug_rot=None, aug_mode=0,
+            overreg=1.025, ssl_lambda=1.0, unsup="ce", want_grad=True, cut_bits=None, extras=True):
+        """Raw tensors in, dict of raw tensors out (no autograd: see ``semiuhpe_b200.agent.ssl_loss``)."""
+        L9, G9 = as_records(out_l, "fisher_out"), as_records(gt_l, "gt")
+        b_l = L9.shape[0]
+        if G9.shape[0] != b_l:
+            raise RuntimeError(f"shape mismatch: {b_l} labeled outputs, {G9.shape[0]} labels")
+        b_u = 0
+        W9 = S9 = R9 = None
+        if pred_weak is not None:
+            W9, S9 = as_records(pred_weak, "pred_weak"), as_records(pred_strong, "pred_strong")
+            b_u = W9.shape[0]
+            if S9.shape[0] != b_u:
+                raise RuntimeError(f"shape mismatch: {b_u} teacher outputs, {S9.shape[0]} student outputs")
+            if aug_rot is not None:
+                R9 = as_records(aug_rot, "aug_rot_mat")
+                if R9.shape[0] != b_u:
+                    raise RuntimeError(f"shape mismatch: {b_u} teacher outputs, {R9.shape[0]} augmentation rotations")
+        if b_l == 0 or b_l > self.max_l or b_u > self.max_u:
+            raise ValueError(f"ssl step of {b_l}+{b_u} rows exceeds the handle's capacity {self.max_l}+{self.max_u} (or is empty)")
+        if unsup not in ("ce", "nll"):
+            raise ValueError(f"unknown unsupervised loss {unsup!r}")
+        dev = L9.device
+        # one allocation for every fp32 output
+        sizes = [4, b_l * 9 if want_grad else 0, b_u * 9 if want_grad else 0]
+        if extras:
+            sizes += [b_l * 9, b_u, b_u * 9, b_l, b_u]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        parts, off = [], 0
+        for sz in sizes:
+            parts.append(flat[off:off + sz] if sz else None)
+            off += sz
+        losses, grad_l, grad_s = parts[:3]
+        rest = ent = pseudo = nll_l = loss_u = mask = None
+        if extras:
+            rest, ent, pseudo, nll_l, loss_u = parts[3:]
+            mask = torch.empty(b_u, dtype=torch.bool, device=dev) if b_u else None
+        thr_dev, thr_host = None, 0.0
+        if isinstance(conf_thres, SelectWorkspace):
+            thr_dev = conf_thres.threshold_ptr()
+        elif isinstance(conf_thres, torch.Tensor):
+            thr_dev = ptr(conf_thres.detach().reshape(-1).to(torch.float32))
+        else:
+            thr_host = float(conf_thres)
+        with on_device(dev) as idx:
+            status = _status_word(dev)
+            check(lib().suhpe_ssl_step_f32(
+                self._h, ptr(L9), ptr(G9), b_l, ptr(W9), ptr(S9), b_u, ptr(R9), int(aug_mode), thr_dev, thr_host,
+                float(overreg), float(ssl_lambda), 0 if unsup == "ce" else 1, _cut(cut_bits),
+                ptr(losses), ptr(grad_l), ptr(grad_s), ptr(rest), ptr(ent), ptr(mask), ptr(pseudo), ptr(nll_l), ptr(loss_u),
+                ptr(status), stream(idx)), "ssl_step")
+        _raise_from_status(status, "ssl_step")
+        out = dict(losses=losses, grad_l=None if grad_l is None else grad_l.view(b_l, 9),
+                   grad_strong=None if grad_s is None else grad_s.view(b_u, 9))
+        if extras:
+            out.update(pred_orth=rest.view(b_l, 3, 3), entropy=ent, mask=mask, pseudo=None if pseudo is None else pseudo.view(b_u, 3, 3),
+                       losses_l=nll_l, losses_u=loss_u)
+        return out

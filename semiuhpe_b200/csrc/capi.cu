@@ -2,6 +2,7 @@
 // No torch types, no exceptions, no hidden synchronisation (except the _host
 // pipeline and suhpe_select_read, which return host values).
 #include "../../include/semiuhpe_b200.h"
+#include "../../include/semiuhpe_b200_probe.h"
 #include "kernels.cuh"
 
 #include <new>
@@ -17,8 +18,7 @@ static_assert(kHistBinsMax == SUHPE_HIST_BINS, "histogram width is part of the A
 static_assert(kStatusNonFinite == SUHPE_STATUS_NONFINITE && kStatusTraceRange == SUHPE_STATUS_TRACE_RANGE &&
               kStatusNonFiniteCE == SUHPE_STATUS_NONFINITE_CE, "status bits");
 
-// negligible-node cut of the Fisher quadrature (see cut_threshold in so3_math.cuh); process-wide
-static int g_cut_bits = 26;
+inline int clamp_cut_bits(int32_t bits) { return bits < 0 ? 0 : (bits > 60 ? 60 : (int)bits); }
 
 inline int rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
 inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -169,6 +169,8 @@ struct suhpe_pipeline {
     // kBuffers chunk buffers, so the two copy engines and the SMs all stay busy at once.
     static constexpr int kBuffers = 4;
     long long max_n, chunk;
+    int cut_bits;
+    bool rec_k[kBuffers], rec_out[kBuffers];   // ev_k / ev_out of this buffer have been recorded (in any call)
     cudaStream_t s_in, s_k, s_out;
     cudaEvent_t ev_in[kBuffers], ev_k[kBuffers], ev_out[kBuffers], ev_user;
     float *dA[kBuffers], *dR[kBuffers], *dGrad[kBuffers], *dNll[kBuffers];
@@ -179,6 +181,21 @@ struct suhpe_pipeline {
     int* dStatus;
     SelectState* hState;     // pinned
     int* hStatus;            // pinned
+};
+
+// ---- SSL loss head -------------------------------------------------------------
+struct suhpe_ssl_step {
+    long long max_l, max_u;
+    cudaStream_t s_a, s_b;                  // forked branches (the caller's stream carries the teacher branch)
+    cudaEvent_t ev_fork, ev_a, ev_b;
+    float* nll_l;                           // (max_l)
+    float* ent;                             // (max_u)
+    float* work;                            // (10 * max_u): G1 | S2 | G2 | H2, the fisher_CE workspace layout
+    float* adjusted;                        // (max_u,9)
+    float* pseudo;                          // (max_u,9)
+    float* loss_u;                          // (max_u)
+    uint8_t* mask;                          // (max_u)
+    unsigned long long* kept;
 };
 
 extern "C" {
@@ -192,13 +209,6 @@ const char* suhpe_error_string(int code) {
     return "unknown";
 }
 
-int suhpe_set_quadrature_cut_bits(int bits) {
-    if (bits > 60) return SUHPE_EINVAL;
-    const int old = g_cut_bits;
-    g_cut_bits = bits < 0 ? 0 : bits;
-    return old;
-}
-
 int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U, float* V,
                          int* status, void* stream) {
     if (n < 0 || (n > 0 && !A)) return SUHPE_EINVAL;
@@ -206,30 +216,30 @@ int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U
     return rc(launch_proper_svd(p, st(stream)));
 }
 
-int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg,
+int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg, int32_t cut_bits,
                            float* nll, float* grad, float* Rout, float* entropy, float* logC,
                            float* S, float* G, uint64_t* hist, int* status, void* stream) {
-    if (n < 0 || (n > 0 && !A) || (hist && !entropy)) return SUHPE_EINVAL;
+    if (n < 0 || (n > 0 && !A)) return SUHPE_EINVAL;
     FisherArgs p{};
     p.A = A; p.Rgt = Rgt; p.n = (long long)n; p.overreg = overreg;
     p.nll = nll; p.grad = grad; p.Rout = Rout; p.entropy = entropy; p.logC = logC; p.S = S; p.G = G;
     p.hist = reinterpret_cast<unsigned long long*>(hist); p.status = status;
-    p.cut_bits = g_cut_bits;
+    p.cut_bits = clamp_cut_bits(cut_bits);
     return rc(launch_fisher_fused(p, st(stream)));
 }
 
-int suhpe_fisher_from_s_f32(const float* S, int64_t n, float* logC, float* G, float* entropy,
+int suhpe_fisher_from_s_f32(const float* S, int64_t n, int32_t cut_bits, float* logC, float* G, float* entropy,
                             int* status, void* stream) {
     if (n < 0 || (n > 0 && !S)) return SUHPE_EINVAL;
     FisherArgs p{};
     p.Sin = S; p.n = (long long)n; p.overreg = 1.0f;
     p.logC = logC; p.G = G; p.entropy = entropy; p.status = status;
-    p.cut_bits = g_cut_bits;
+    p.cut_bits = clamp_cut_bits(cut_bits);
     return rc(launch_fisher_fused(p, st(stream)));
 }
 
-static int fisher_ce_impl(const float* A1, const float* G1_given, const float* A2, int64_t n, float* ce, float* gradA2,
-                          float* workspace, int* status, void* stream) {
+static int fisher_ce_impl(const float* A1, const float* G1_given, const float* A2, int64_t n, int cut_bits,
+                          const uint8_t* keep, float* ce, float* gradA2, float* workspace, int* status, void* stream) {
     if (n < 0 || (n > 0 && (!A1 || !A2 || !ce || !workspace))) return SUHPE_EINVAL;
     if (n == 0) return 0;
     float* G1 = workspace;                     // (n,3)
@@ -239,27 +249,35 @@ static int fisher_ce_impl(const float* A1, const float* G1_given, const float* A
     cudaError_t e = cudaSuccess;
     if (!G1_given) {
         FisherArgs t{};
-        t.A = A1; t.n = (long long)n; t.overreg = 1.0f; t.G = G1; t.status = status; t.cut_bits = g_cut_bits;
+        t.A = A1; t.n = (long long)n; t.overreg = 1.0f; t.G = G1; t.status = status; t.keep = keep; t.cut_bits = cut_bits;
         e = launch_fisher_fused(t, st(stream));
         if (e != cudaSuccess) return rc(e);
     }
     FisherArgs q{};
-    q.A = A2; q.n = (long long)n; q.overreg = 1.0f; q.S = S2; q.G = G2; q.entropy = H2; q.status = status; q.cut_bits = g_cut_bits;
+    q.A = A2; q.n = (long long)n; q.overreg = 1.0f; q.S = S2; q.G = G2; q.entropy = H2; q.status = status; q.keep = keep;
+    q.cut_bits = cut_bits;
     e = launch_fisher_fused(q, st(stream));
     if (e != cudaSuccess) return rc(e);
-    FisherCeArgs c{A1, A2, (long long)n, G1_given ? G1_given : G1, S2, G2, H2, ce, gradA2, status};
+    FisherCeArgs c{A1, A2, (long long)n, G1_given ? G1_given : G1, S2, G2, H2, ce, gradA2, status, keep};
     return rc(launch_fisher_ce_close(c, st(stream)));
 }
 
-int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, float* ce, float* gradA2,
-                        float* workspace, int* status, void* stream) {
-    return fisher_ce_impl(A1, nullptr, A2, n, ce, gradA2, workspace, status, stream);
+int suhpe_fisher_ce_f32(const float* A1, const float* A2, int64_t n, int32_t cut_bits, const uint8_t* keep,
+                        float* ce, float* gradA2, float* workspace, int* status, void* stream) {
+    return fisher_ce_impl(A1, nullptr, A2, n, clamp_cut_bits(cut_bits), keep, ce, gradA2, workspace, status, stream);
 }
 
-int suhpe_fisher_ce_with_g1_f32(const float* A1, const float* G1, const float* A2, int64_t n, float* ce, float* gradA2,
-                                float* workspace, int* status, void* stream) {
+int suhpe_fisher_ce_with_g1_f32(const float* A1, const float* G1, const float* A2, int64_t n, int32_t cut_bits,
+                                const uint8_t* keep, float* ce, float* gradA2, float* workspace, int* status,
+                                void* stream) {
     if (n > 0 && !G1) return SUHPE_EINVAL;
-    return fisher_ce_impl(A1, G1, A2, n, ce, gradA2, workspace, status, stream);
+    return fisher_ce_impl(A1, G1, A2, n, clamp_cut_bits(cut_bits), keep, ce, gradA2, workspace, status, stream);
+}
+
+int suhpe_scale_rows_f32(const float* in, int64_t n, int32_t width, const float* row_weight,
+                         const float* scalar_weight, const uint8_t* keep, float* out, void* stream) {
+    if (n < 0 || width <= 0 || (n > 0 && (!in || !out))) return SUHPE_EINVAL;
+    return rc(launch_scale_rows(in, (long long)n, (int)width, row_weight, scalar_weight, keep, out, st(stream)));
 }
 
 int suhpe_rotate_adjust_f32(const float* pred, const float* aug_rot, int64_t n, int32_t mode, float* out, void* stream) {
@@ -379,14 +397,14 @@ int suhpe_pipeline_destroy(suhpe_pipeline* p) {
     return 0;
 }
 
-int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk) {
+int suhpe_pipeline_create(suhpe_pipeline** out, int64_t max_n, int64_t chunk, int32_t cut_bits) {
     if (!out || max_n <= 0 || chunk <= 0) return SUHPE_EINVAL;
     suhpe_pipeline* p = new (std::nothrow) suhpe_pipeline();
     if (!p) return SUHPE_EINVAL;
     memset(p, 0, sizeof(*p));
     if (chunk > max_n) chunk = max_n;
     chunk = (chunk + 127) & ~127LL;               // chunk bases (and quarter chunks) stay 16-byte aligned: 32 records = 1152 B
-    p->max_n = max_n; p->chunk = chunk;
+    p->max_n = max_n; p->chunk = chunk; p->cut_bits = clamp_cut_bits(cut_bits);
     cudaError_t e = cudaSuccess;
     auto A = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(q, bytes); };
     auto S = [&](cudaStream_t* s) { if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); };
@@ -444,28 +462,31 @@ int suhpe_fisher_pool_host(suhpe_pipeline* p, const float* A_host, const float* 
         else cnt = (c == nchunks - 1) ? q : 2 * q;
         const long long this_base = base;
         base += cnt;
-        // inputs: the buffer is free once the kernel of its previous chunk has run
-        if (c >= NB) CK(cudaStreamWaitEvent(p->s_in, p->ev_k[b], 0));
+        // inputs: the buffer is free once the kernel of its previous use -- in this call or an earlier one
+        // that was not followed by suhpe_pipeline_sync -- has run
+        if (p->rec_k[b]) CK(cudaStreamWaitEvent(p->s_in, p->ev_k[b], 0));
         CK(cudaMemcpyAsync(p->dA[b], A_host + this_base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
         if (Rgt_host) CK(cudaMemcpyAsync(p->dR[b], Rgt_host + this_base * 9, (size_t)cnt * 36, cudaMemcpyHostToDevice, p->s_in));
         CK(cudaEventRecord(p->ev_in[b], p->s_in));
         // kernel: after its inputs landed and the previous outputs of this buffer were drained
         CK(cudaStreamWaitEvent(p->s_k, p->ev_in[b], 0));
-        if (c >= NB) CK(cudaStreamWaitEvent(p->s_k, p->ev_out[b], 0));
+        if (p->rec_out[b]) CK(cudaStreamWaitEvent(p->s_k, p->ev_out[b], 0));
         FisherArgs a{};
         a.A = p->dA[b]; a.Rgt = Rgt_host ? p->dR[b] : nullptr; a.n = cnt; a.overreg = overreg;
         a.nll = nll_host ? p->dNll[b] : nullptr;
         a.grad = grad_host ? p->dGrad[b] : nullptr;
         a.entropy = ent_dev + this_base;
-        a.hist = reinterpret_cast<unsigned long long*>(hist_dev); a.status = status_dev; a.cut_bits = g_cut_bits;
+        a.hist = reinterpret_cast<unsigned long long*>(hist_dev); a.status = status_dev; a.cut_bits = p->cut_bits;
         CK(launch_fisher_fused(a, p->s_k));
         CK(cudaEventRecord(p->ev_k[b], p->s_k));
+        if (e == cudaSuccess) p->rec_k[b] = true;
         // outputs
         CK(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0));
         if (nll_host) CK(cudaMemcpyAsync(nll_host + this_base, p->dNll[b], (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
         if (grad_host) CK(cudaMemcpyAsync(grad_host + this_base * 9, p->dGrad[b], (size_t)cnt * 36, cudaMemcpyDeviceToHost, p->s_out));
         if (entropy_host) CK(cudaMemcpyAsync(entropy_host + this_base, ent_dev + this_base, (size_t)cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
         CK(cudaEventRecord(p->ev_out[b], p->s_out));
+        if (e == cudaSuccess) p->rec_out[b] = true;
     }
     if (external) CK(cudaStreamWaitEvent(user, p->ev_k[(nchunks - 1) % NB], 0));
 #undef CK
@@ -509,6 +530,120 @@ int suhpe_fisher_filter_host(suhpe_pipeline* p, const float* A_host, const float
     if (threshold) *threshold = p->hState->threshold;
     if (kept) *kept = p->hState->kept;
     return (*p->hStatus & SUHPE_STATUS_NONFINITE) ? 1 : 0;   // >0: completed, non-finite input seen
+}
+
+// ---- SSL loss head -----------------------------------------------------------------
+int suhpe_ssl_step_destroy(suhpe_ssl_step* c) {
+    if (!c) return 0;
+    if (c->s_a) cudaStreamDestroy(c->s_a);
+    if (c->s_b) cudaStreamDestroy(c->s_b);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    cudaFree(c->nll_l); cudaFree(c->ent); cudaFree(c->work); cudaFree(c->adjusted); cudaFree(c->pseudo);
+    cudaFree(c->loss_u); cudaFree(c->mask); cudaFree(c->kept);
+    delete c;
+    return 0;
+}
+
+int suhpe_ssl_step_create(suhpe_ssl_step** out, int64_t max_labeled, int64_t max_unlabeled) {
+    if (!out || max_labeled <= 0 || max_unlabeled < 0) return SUHPE_EINVAL;
+    suhpe_ssl_step* c = new (std::nothrow) suhpe_ssl_step();
+    if (!c) return SUHPE_EINVAL;
+    memset(c, 0, sizeof(*c));
+    c->max_l = max_labeled; c->max_u = max_unlabeled;
+    const size_t mu = (size_t)(max_unlabeled > 0 ? max_unlabeled : 1);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(q, bytes); };
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_a, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_b, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming);
+    A((void**)&c->nll_l, (size_t)max_labeled * 4);
+    A((void**)&c->ent, mu * 4); A((void**)&c->work, mu * 4 * SUHPE_FISHER_CE_WORKSPACE_FLOATS);
+    A((void**)&c->adjusted, mu * 36); A((void**)&c->pseudo, mu * 36); A((void**)&c->loss_u, mu * 4);
+    A((void**)&c->mask, mu); A((void**)&c->kept, sizeof(unsigned long long));
+    if (e != cudaSuccess) { suhpe_ssl_step_destroy(c); return rc(e); }
+    *out = c;
+    return 0;
+}
+
+int suhpe_ssl_step_f32(suhpe_ssl_step* c, const float* out_l, const float* gt_l, int64_t b_l,
+                       const float* pred_weak, const float* pred_strong, int64_t b_u,
+                       const float* aug_rot, int32_t aug_mode, const float* conf_thres_dev, float conf_thres_host,
+                       float overreg, float ssl_lambda, int32_t unsup_kind, int32_t cut_bits,
+                       float* losses, float* grad_l, float* grad_strong,
+                       float* Rest_l, float* entropy, uint8_t* mask, float* pseudo, float* losses_l, float* losses_u,
+                       int* status, void* stream) {
+    if (!c || !losses || b_l <= 0 || b_l > c->max_l || b_u < 0 || b_u > c->max_u || !out_l || !gt_l) return SUHPE_EINVAL;
+    if (b_u > 0 && (!pred_weak || !pred_strong)) return SUHPE_EINVAL;
+    if (unsup_kind < 0 || unsup_kind > 1 || (aug_rot && (aug_mode < 0 || aug_mode > 1))) return SUHPE_EINVAL;
+    const int bits = clamp_cut_bits(cut_bits);
+    cudaStream_t S = st(stream);
+    float* nll_l = losses_l ? losses_l : c->nll_l;
+    float* ent = entropy ? entropy : c->ent;
+    uint8_t* msk = mask ? mask : c->mask;
+    float* pse = pseudo ? pseudo : c->pseudo;
+    cudaError_t e = cudaSuccess;
+#define CK(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    // fork: the supervised quadrature (and, for 'ce', the student's unlabeled quadrature) run beside the teacher branch
+    CK(cudaEventRecord(c->ev_fork, S));
+    CK(cudaStreamWaitEvent(c->s_a, c->ev_fork, 0));
+    {
+        FisherArgs a{};
+        a.A = out_l; a.Rgt = gt_l; a.n = (long long)b_l; a.overreg = overreg; a.nll = nll_l; a.grad = grad_l; a.Rout = Rest_l;
+        a.status = status; a.cut_bits = bits;
+        CK(launch_fisher_fused(a, c->s_a));
+        CK(cudaEventRecord(c->ev_a, c->s_a));
+    }
+    if (b_u > 0) {
+        float* G1 = c->work;
+        if (unsup_kind == 0) {
+            CK(cudaStreamWaitEvent(c->s_b, c->ev_fork, 0));
+            FisherArgs q{};                       // student, unlabeled: the statistics fisher_CE needs of the prediction
+            q.A = pred_strong; q.n = (long long)b_u; q.overreg = 1.0f;
+            q.S = c->work + 3 * b_u; q.G = c->work + 6 * b_u; q.entropy = c->work + 9 * b_u;
+            q.status = nullptr;                   // non-finite rows are reported by the closing kernel, for kept rows only
+            q.cut_bits = bits;
+            CK(launch_fisher_fused(q, c->s_b));
+            CK(cudaEventRecord(c->ev_b, c->s_b));
+        }
+        FisherArgs t{};                           // teacher: entropy (src/agent.py:139) and, for 'ce', G1 = d logC/dS
+        t.A = pred_weak; t.n = (long long)b_u; t.overreg = 1.0f; t.entropy = ent; t.G = unsup_kind == 0 ? G1 : nullptr;
+        t.status = status; t.cut_bits = bits;
+        CK(launch_fisher_fused(t, S));
+        CK(cudaMemsetAsync(c->kept, 0, sizeof(unsigned long long), S));
+        CK(launch_mask(ent, (long long)b_u, conf_thres_dev, conf_thres_host, msk, c->kept, S));
+        const float* adjusted = pred_weak;
+        if (aug_rot) {
+            CK(launch_rotate_adjust(pred_weak, aug_rot, (long long)b_u, (int)aug_mode, c->adjusted, S));
+            adjusted = c->adjusted;
+        }
+        if (unsup_kind == 1 || pseudo) {
+            SvdArgs sv{adjusted, (long long)b_u, pse, nullptr, nullptr, nullptr, status, false};
+            CK(launch_proper_svd(sv, S));
+        }
+        if (unsup_kind == 0) {
+            CK(cudaStreamWaitEvent(S, c->ev_b, 0));
+            FisherCeArgs ce{adjusted, pred_strong, (long long)b_u, G1, c->work + 3 * b_u, c->work + 6 * b_u, c->work + 9 * b_u,
+                            c->loss_u, grad_strong, status, msk};
+            CK(launch_fisher_ce_close(ce, S));
+        } else {
+            FisherArgs q{};                       // 'nll': the student's Fisher NLL against the projected pseudo labels
+            q.A = pred_strong; q.Rgt = pse; q.n = (long long)b_u; q.overreg = overreg; q.nll = c->loss_u; q.grad = grad_strong;
+            q.status = status; q.keep = msk; q.cut_bits = bits;
+            CK(launch_fisher_fused(q, S));
+        }
+    }
+    CK(cudaStreamWaitEvent(S, c->ev_a, 0));
+    SslFinalizeArgs f{};
+    f.nll_l = nll_l; f.b_l = (long long)b_l; f.grad_l = grad_l;
+    f.loss_u = c->loss_u; f.b_u = (long long)b_u; f.grad_u = b_u > 0 ? grad_strong : nullptr;
+    f.mask = msk; f.kept = c->kept; f.ssl_lambda = ssl_lambda; f.losses = losses; f.losses_u_out = b_u > 0 ? losses_u : nullptr;
+    CK(launch_ssl_finalize(f, S));
+#undef CK
+    return rc(e);
 }
 
 }  // extern "C"

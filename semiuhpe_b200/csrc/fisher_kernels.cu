@@ -22,7 +22,8 @@
 //            MUFU.EX2 per node is the only SFU work; pairs past the end of a run (the tail of its
 //            last pass) are dropped by one select per pair on the ALU pipe
 //   phase 3  thread-per-sample : closing arithmetic, gradient
-//            -R_gt + overreg * U diag(g) V^T, entropy, staged float4 stores
+//            -R_gt + overreg * U diag(g) V^T, entropy, staged float4 stores; with `hist` the first
+//            radix-select digit of the entropy key is counted right here (warp-aggregated RED.ADD)
 // Geometry: one persistent CTA of 24 warps per SM (79 registers: the per-sample state of phase 3
 // rides through phase 2 in shared memory), 27 KB of node tables shared by the CTA + 8.25 KB of
 // scratch per warp in dynamic shared memory (225 KB).
@@ -401,7 +402,7 @@ fisher_fused_kernel(FisherArgs p) {
 #pragma unroll
                     for (int k = 0; k < 9; ++k) dot = fmaf(A[k], ws.r[sj * 9 + k], dot);
                 }
-                if (!proper_svd3(A, U, V, s)) bad = true;          // (the lanes of a spread sample repeat the SVD: no exchange needed)
+                if (!proper_svd3(A, U, V, s) && (p.keep == nullptr || p.keep[base + sj] != 0)) bad = true;   // (the lanes of a spread sample repeat the SVD: no exchange needed)
                 if (fam0 == 0) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -535,6 +536,14 @@ fisher_fused_kernel(FisherArgs p) {
             const long long i = base + lane;
             if (p.nll) p.nll[i] = fmaf(p.overreg, st.logC, -dot);
             if (p.entropy) p.entropy[i] = st.entropy;
+            if (p.hist) {
+                // first radix-select pass, in the kernel: the top 11 key bits of the entropy this lane just
+                // produced.  Entropies of a tile fall into a handful of bins, so the lanes that share a bin
+                // elect a leader and one RED.ADD per (tile, bin) goes to the 2048 global counters.
+                const unsigned bin = entropy_key(st.entropy) >> kHistShift1;
+                const unsigned peers = __match_any_sync(__activemask(), bin);
+                if ((int)(__ffs(peers) - 1) == lane) atomicAdd(p.hist + bin, (unsigned long long)__popc(peers));
+            }
             if (p.logC) p.logC[i] = st.logC;
             if (p.S) { p.S[3 * i] = s[0]; p.S[3 * i + 1] = s[1]; p.S[3 * i + 2] = s[2]; }
             if (p.G) { p.G[3 * i] = st.g[0]; p.G[3 * i + 1] = st.g[1]; p.G[3 * i + 2] = st.g[2]; }
@@ -651,7 +660,11 @@ fisher_ce_close_kernel(FisherCeArgs p, bool vec_ok) {
         load_tile(ws.r, p.A2 + base * 9, count, vec_ok, lane);
         __syncwarp();
         float grad[9];
-        if (lane < count) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) grad[k] = 0.0f;
+        const bool kept_row = lane < count && (p.keep == nullptr || p.keep[base + lane] != 0);
+        if (lane < count && !kept_row) p.ce[base + lane] = 0.0f;      // filtered row: the reference never evaluates it
+        if (kept_row) {
             const long long i = base + lane;
             float A[9], U1[9], V1[9], U2[9], V2[9], s1[3], s2[3];
 #pragma unroll
@@ -845,25 +858,31 @@ cudaError_t launch_body_probe(float* sink, int variant, int iters, int blocks, c
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-static int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+// per-device launch facts, looked up once per device (the library holds no other state)
+int device_sm_count() {
+    constexpr int kMaxDevices = 64;
+    static int sms[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    int v = sms[dev];
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;                         // benign race: every writer stores the same value
     }
-    return sms;
+    return v;
 }
+
+static int sm_count() { return device_sm_count(); }
 
 cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int sms = sm_count();
     constexpr size_t kSmem = sizeof(QuadTables) + sizeof(WarpScratch) * kWarpsPerBlock;
     static_assert(kSmem <= 227 * 1024, "fisher_fused_kernel shared memory exceeds one SM");
-    const bool forward_only = !(p.grad || p.entropy || p.G);
+    const bool forward_only = !(p.grad || p.entropy || p.G || p.hist);
     auto kernel = forward_only ? fisher_fused_kernel<1> : fisher_fused_kernel<3>;
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    static unsigned long long attr_done[2] = {0ull, 0ull};
+    cudaError_t err = allow_dynamic_smem(kernel, kSmem, attr_done[forward_only ? 0 : 1]);
     if (err != cudaSuccess) return err;
     // one persistent CTA of 24 warps per SM (the node tables are shared by the whole CTA); small
     // batches get one sample per warp on as many SMs as that takes (latency)
@@ -878,10 +897,7 @@ cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream) {
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     p.vec_ok = aligned(p.A) && aligned(p.Rgt) && aligned(p.grad) && aligned(p.Rout);
     kernel<<<(unsigned)blocks, kThreads, kSmem, stream>>>(p);
-    err = cudaGetLastError();
-    // first radix-select pass over the entropies just written (they are still L2-resident)
-    if (err == cudaSuccess && p.hist) err = launch_select_hist_accumulate(p.entropy, p.n, p.hist, stream);
-    return err;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rotate_adjust(const float* P, const float* Raug, long long n, int mode, float* out, cudaStream_t stream) {

@@ -29,8 +29,9 @@ struct FisherArgs {
     float* logC;           // (n)   log normaliser                 | nullptr
     float* S;              // (n,3) proper singular values         | nullptr
     float* G;              // (n,3) d logC / d S                   | nullptr
-    unsigned long long* hist;  // (2048) += histogram of the top 11 key bits of entropy | nullptr
+    unsigned long long* hist;  // (2048) += histogram of the top 11 key bits of entropy, counted in the kernel | nullptr
     int* status;           // |= kStatus* | nullptr
+    const uint8_t* keep;   // (n) rows with keep == 0 never raise a status bit (their outputs are still written) | nullptr
     int cut_bits;          // negligible-node cut: skipped mass < 2^-cut_bits of the normaliser sum; <= 0 = off
     long long full_rounds; // set by the launcher: rounds of one 32-sample tile per warp
     int samples_per_warp;  // set by the launcher: samples per warp in the closing round (0..32)
@@ -84,11 +85,43 @@ struct FisherCeArgs {
     float* ce;             // (n)
     float* grad;           // (n,9) d ce_i / d A2_i | nullptr
     int* status;
+    const uint8_t* keep;   // (n) rows with keep == 0 give ce = 0, grad = 0 and no status bit | nullptr = all rows
 };
 
+int device_sm_count();      // SM count of the current device (cached per device)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch;
+// `done_mask` is a static word owned by the call site, one bit per device
+template <typename K>
+inline cudaError_t allow_dynamic_smem(K kernel, size_t bytes, unsigned long long& done_mask) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_mask & bit) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err == cudaSuccess) done_mask |= bit;     // benign race: setting the attribute twice is harmless
+    return err;
+}
 cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream);
 cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream);
 cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream);
+// out[i,:] = in[i,:] * row_weight[i] * *scalar_weight, zero rows where keep[i] == 0 (each factor nullable)
+cudaError_t launch_scale_rows(const float* in, long long n, int width, const float* row_weight, const float* scalar_weight,
+                              const uint8_t* keep, float* out, cudaStream_t stream);
+// closing reduction of the SSL loss head (see suhpe_ssl_step_f32): means, loss_all, scaled gradients
+struct SslFinalizeArgs {
+    const float* nll_l; long long b_l;      // per-sample supervised losses
+    float* grad_l;                          // (b_l,9) in: d nll_i/d out_i, out: d loss_all / d out_l
+    const float* loss_u; long long b_u;     // per-sample unsupervised losses (any value on filtered rows)
+    float* grad_u;                          // (b_u,9) in: d l_i / d pred_strong_i, out: d loss_all / d pred_strong
+    const uint8_t* mask;                    // (b_u)
+    const unsigned long long* kept;         // mask popcount
+    float ssl_lambda;
+    float* losses;                          // [4] loss_sup, unsuper_loss, mask_ratio, loss_all
+    float* losses_u_out;                    // (b_u) masked per-sample losses | nullptr
+};
+cudaError_t launch_ssl_finalize(SslFinalizeArgs a, cudaStream_t stream);
 cudaError_t launch_rotate_adjust(const float* P, const float* Raug, long long n, int mode, float* out, cudaStream_t stream);
 cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream);
 
@@ -121,8 +154,6 @@ struct SelectState {
 
 cudaError_t launch_select_hist(const float* e, long long n, int pass, const SelectState* state,
                                unsigned long long* hist, cudaStream_t stream);
-// pass-1 histogram ADDED into hist (no clear): the "fused" first pass of K2's hist output
-cudaError_t launch_select_hist_accumulate(const float* e, long long n, unsigned long long* hist, cudaStream_t stream);
 // hist_parts: (parts, bins) gathered histograms, summed on the fly
 cudaError_t launch_select_scan(const unsigned long long* hist_parts, int parts, int pass,
                                SelectState* state, cudaStream_t stream);

@@ -359,16 +359,17 @@ laplace_kernel(LaplaceArgs p, int chunk, int stride) {
 cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     if (p.N <= 0) return cudaErrorInvalidValue;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sm_count();
     const bool per_thread = p.n >= (long long)sms * kLapThreads;
     cudaError_t err;
     if (per_thread) {
         const int chunk = p.N < kStreamChunk ? ((p.N + 3) & ~3) : kStreamChunk;
         const size_t smem = ((size_t)chunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);
         auto kernel = p.grad ? laplace_stream_kernel<true> : laplace_stream_kernel<false>;
-        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // allowed once per device at the largest size any call can ask for
+        constexpr size_t kSmemMax = ((size_t)kStreamChunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);
+        static unsigned long long attr_done[2] = {0ull, 0ull};
+        err = allow_dynamic_smem(kernel, kSmemMax, attr_done[p.grad ? 1 : 0]);
         if (err != cudaSuccess) return err;
         const long long tiles = (p.n + kStreamThreads - 1) / kStreamThreads;
         const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);    // one persistent CTA per SM
@@ -377,7 +378,8 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
         const int chunk = p.N < kGridChunk ? p.N : kGridChunk;
         const int stride = (chunk + 3) & ~3;
         const size_t smem = (size_t)9 * stride * sizeof(float);
-        err = cudaFuncSetAttribute(laplace_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static unsigned long long attr_done32 = 0ull;
+        err = allow_dynamic_smem(laplace_kernel<32>, (size_t)9 * kGridChunk * sizeof(float), attr_done32);
         if (err != cudaSuccess) return err;
         // spread the samples over all SMs: up to 8 per block pass, as few as 1 when the batch is tiny
         const long long tiles = (p.n + (kLapThreads / 32) - 1) / (kLapThreads / 32);

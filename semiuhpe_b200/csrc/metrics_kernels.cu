@@ -191,12 +191,11 @@ metrics_kernel(MetricsArgs p, bool vec_ok) {
 
 cudaError_t launch_metrics(MetricsArgs p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sm_count();
     constexpr size_t kSmem = sizeof(MetWarp) * kMetWarps;
     static_assert(kSmem * kMetCtasPerSm <= 227 * 1024, "metrics_kernel: shared memory of the resident CTAs exceeds one SM");
-    cudaError_t err = cudaFuncSetAttribute(metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    static unsigned long long attr_done = 0ull;
+    cudaError_t err = allow_dynamic_smem(metrics_kernel, kSmem, attr_done);
     if (err != cudaSuccess) return err;
     const long long tiles = (p.n + 31) / 32;
     long long blocks = (tiles + kMetWarps - 1) / kMetWarps;

@@ -189,9 +189,7 @@ mask_kernel(const float* __restrict__ e, long long n, const float* __restrict__ 
 }
 
 int stream_blocks(long long items_per_block_pass, long long n) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sm_count();
     long long want = (n + items_per_block_pass - 1) / items_per_block_pass;
     const long long cap = (long long)sms * 4;
     if (want > cap) want = cap;
@@ -214,14 +212,6 @@ cudaError_t launch_select_hist(const float* e, long long n, int pass, const Sele
     const bool vec_ok = (reinterpret_cast<uintptr_t>(e) & 15u) == 0;
     const int blocks = stream_blocks((long long)kSelThreads * 4 * 4, n);
     select_hist_kernel<<<blocks, kSelThreads, 0, stream>>>(e, n, pass, state, hist, vec_ok);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_select_hist_accumulate(const float* e, long long n, unsigned long long* hist, cudaStream_t stream) {
-    if (n <= 0) return cudaSuccess;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(e) & 15u) == 0;
-    const int blocks = stream_blocks((long long)kSelThreads * 4 * 4, n);
-    select_hist_kernel<<<blocks, kSelThreads, 0, stream>>>(e, n, 1, nullptr, hist, vec_ok);
     return cudaGetLastError();
 }
 

@@ -81,3 +81,23 @@ def global_entropy_threshold(entropy_shard, left_ratio, group=None, backend=None
             gathered = local.reshape(1, -1)
         backend.scan(gathered, pass_no)
     return backend.result() if sync else backend
+
+
+def sharded_mean(values, group=None, weights=None):
+    """``losses.mean()`` (src/agent.py:83,163) when the batch is sharded over the ranks of ``group``: the mean of
+    the CONCATENATED per-sample values, identical on every rank -- one all-reduce of (sum, count) in float64, so
+    the integer part (the count) is exact and the sum is the float64 sum of the ranks' float64 partial sums.
+    ``weights`` (same shape, e.g. a keep mask): returns ``sum(values * weights) / total_count`` -- the
+    masked-mean-times-mask-ratio form of the unsupervised loss (:163-166).  Differentiable: each rank's
+    gradient is ``weights / total_count``, which is what the single-process mean gives its slice."""
+    v = values.reshape(-1)
+    w = None if weights is None else weights.reshape(-1).to(v.dtype)
+    local = (v if w is None else torch.where(w != 0, v, torch.zeros((), dtype=v.dtype, device=v.device)) * w)
+    stats = torch.stack((local.detach().to(torch.float64).sum(),
+                         torch.tensor(float(v.numel()), dtype=torch.float64, device=v.device)))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, group=group)
+    total = stats[1].clamp(min=1.0)
+    mean = (stats[0] / total).to(v.dtype)
+    # value from the exact global statistics, gradient through this rank's slice only
+    return mean.detach() + (local.sum() - local.sum().detach()) / total.to(v.dtype)

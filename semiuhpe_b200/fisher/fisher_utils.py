@@ -21,12 +21,13 @@ class _FisherNLL(torch.autograd.Function):
     """nll_i = -<A_i,R_i> + overreg*logC(S_i);  d nll_i/dA_i from the same launch."""
 
     @staticmethod
-    def forward(ctx, A, R, overreg, want_rot):
+    def forward(ctx, A, R, overreg, want_rot, keep):
         need_grad = ctx.needs_input_grad[0]
         out = _ops.fisher_fused(A, R, overreg, nll=True, grad=need_grad, rot=want_rot, what="KL_Fisher")
         if need_grad:
             ctx.save_for_backward(out["grad"])
         ctx.a_shape = A.shape
+        ctx.keep = keep
         rot = out.get("rot")
         if rot is None:
             rot = torch.empty(0, device=A.device)
@@ -36,19 +37,22 @@ class _FisherNLL(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_nll, _g_rot):
         (grad,) = ctx.saved_tensors
-        return (grad * g_nll.reshape(-1, 1)).view(ctx.a_shape), None, None, None
+        # one launch: saved per-sample gradient x incoming gradient; rows the caller filtered out are exact zeros
+        return _ops.scale_rows(grad, g_nll, keep=ctx.keep).view(ctx.a_shape), None, None, None, None
 
 
-def vmf_loss(net_out, R, overreg=1.05):
-    """(loss (b,), Rest (b,3,3))  -- reference fisher_utils.py:14-18."""
+def vmf_loss(net_out, R, overreg=1.05, keep=None):
+    """(loss (b,), Rest (b,3,3))  -- reference fisher_utils.py:14-18.
+    ``keep`` (extension, optional, (b,) bool): rows a mask filtered out; their gradient is exactly zero whatever
+    the row holds (the reference gathers ``pred[mask]`` before the loss: src/agent.py:157)."""
     A = net_out.view(-1, 3, 3)
-    loss_v, Rest = _FisherNLL.apply(A, R, float(overreg), True)
+    loss_v, Rest = _FisherNLL.apply(A, R, float(overreg), True, keep)
     return loss_v, Rest
 
 
 def KL_Fisher(A, R, overreg=1.05):
     """Matrix-Fisher NLL (b,) -- reference fisher_utils.py:21-36."""
-    loss_v, _ = _FisherNLL.apply(A, R, float(overreg), False)
+    loss_v, _ = _FisherNLL.apply(A, R, float(overreg), False, None)
     return loss_v
 
 
@@ -82,21 +86,22 @@ class _FisherCE(torch.autograd.Function):
     """ce_i and d ce_i / d A2_i from the same three launches."""
 
     @staticmethod
-    def forward(ctx, A1, A2, target_G):
+    def forward(ctx, A1, A2, target_G, keep):
         need_grad = ctx.needs_input_grad[1]
-        out = _ops.fisher_ce(A1, A2, grad=need_grad, target_G=target_G)
+        out = _ops.fisher_ce(A1, A2, grad=need_grad, target_G=target_G, keep=keep)
         if need_grad:
             ctx.save_for_backward(out["grad"])
         ctx.a_shape = A2.shape
+        ctx.keep = keep
         return out["ce"]
 
     @staticmethod
     def backward(ctx, g_ce):
         (grad,) = ctx.saved_tensors
-        return None, (grad * g_ce.reshape(-1, 1)).view(ctx.a_shape), None
+        return None, _ops.scale_rows(grad, g_ce, keep=ctx.keep).view(ctx.a_shape), None, None
 
 
-def fisher_CE(A1, A2, target_G=None):
+def fisher_CE(A1, A2, target_G=None, keep=None):
     """Cross entropy h(f1, f2) of two matrix-Fisher densities, A1 the target and A2 the
     prediction, (b,9)|(b,3,3) x2 -> (b,)  -- reference fisher_utils.py:84-99 (the default
     unsupervised loss, src/agent.py:155).  Differentiable w.r.t. A2 like the reference (through the
@@ -105,8 +110,11 @@ def fisher_CE(A1, A2, target_G=None):
     than a silent zero.  NaN/Inf results raise AssertionError as in the reference (:98).
     ``target_G`` (extension, optional): d logC/dS of the target, (b,3), e.g. the ``G`` output of the
     entropy launch on the teacher prediction -- unchanged by the rotate-augmentation adjustment --
-    which saves the target's quadrature (one K2 launch instead of two)."""
+    which saves the target's quadrature (one K2 launch instead of two).
+    ``keep`` (extension, optional, (b,) bool): the rows the reference would have gathered with
+    ``[mask_fisher]`` before the call (src/agent.py:155).  Filtered rows return 0, get an exactly zero
+    gradient and are not checked: the assert of :98 looks at the kept rows only, as in the reference."""
     if isinstance(A1, torch.Tensor) and A1.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError("fisher_CE: the gradient w.r.t. the target A1 is not implemented "
                                   "(the reference's training loop detaches it, src/agent.py:107)")
-    return _FisherCE.apply(A1, A2, target_G)
+    return _FisherCE.apply(A1, A2, target_G, keep)

@@ -20,7 +20,7 @@ class _LogCF(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (G,) = ctx.saved_tensors
-        return (G * grad.reshape(-1, 1)).view(ctx.in_shape)
+        return _ops.scale_rows(G, grad).view(ctx.in_shape)
 
 
 def logC_F(S):

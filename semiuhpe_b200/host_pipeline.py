@@ -22,14 +22,16 @@ from .agent import pool_index
 
 
 class FisherFilterPipeline:
-    def __init__(self, max_n, chunk=1 << 20, device=0):
+    def __init__(self, max_n, chunk=1 << 20, device=0, cut_bits=None):
         if not torch.cuda.is_available():
             raise RuntimeError("FisherFilterPipeline needs a CUDA device: semiuhpe_b200 has no CPU path")
         self.device = torch.device("cuda", device)
         self.max_n, self.chunk = int(max_n), int(chunk)
         self._h = ctypes.c_void_p()
+        import semiuhpe_b200 as _pkg
+        bits = _pkg.quadrature_cut_bits() if cut_bits is None else int(cut_bits)
         with torch.cuda.device(self.device):
-            _capi.check(_capi.lib().suhpe_pipeline_create(ctypes.byref(self._h), self.max_n, self.chunk),
+            _capi.check(_capi.lib().suhpe_pipeline_create(ctypes.byref(self._h), self.max_n, self.chunk, bits),
                         "pipeline_create")
         self._out = None
 
@@ -65,13 +67,15 @@ class FisherFilterPipeline:
         n = A_host.reshape(-1, 9).shape[0]
         if n > self.max_n:
             raise ValueError(f"pool of {n} exceeds the pipeline capacity {self.max_n}")
-        out = self._buffers(n, want_grad)
+        out = dict(self._buffers(n, want_grad))
+        if not want_grad:
+            out["grad"] = None                      # a cached gradient buffer of an earlier call is not filled (nor copied)
         if group is not None:
             return self._run_sharded(A_host, R_host, n, overreg, left_ratio, want_grad, out,
                                      None if group is True else group)
         k = pool_index(n, left_ratio)
         thr, kept = ctypes.c_float(), ctypes.c_uint64()
-        P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        P = lambda t: None if t is None else t.data_ptr()
         with torch.cuda.device(self.device):
             code = _capi.check(_capi.lib().suhpe_fisher_filter_host(
                 self._h, P(A_host), P(R_host), n, float(overreg), k, P(out["nll"]), P(out["grad"]),
@@ -87,7 +91,7 @@ class FisherFilterPipeline:
         from . import _ops
         from .distributed import global_entropy_threshold
         dev = self.device
-        P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        P = lambda t: None if t is None else t.data_ptr()
         with torch.cuda.device(dev):
             if getattr(self, "_dev", None) is None or self._dev["ent"].numel() != n:
                 self._dev = dict(ent=torch.empty(n, dtype=torch.float32, device=dev),

@@ -5,8 +5,16 @@ predict.py:15, image.py:23, video.py:23, eval_DAD3DHeads.py:14).  Registering
 the mirrors under those names before the reference's own packages are imported
 makes every later ``from src.fisher.fisher_utils import vmf_loss`` resolve to the
 CUDA path; nothing in the reference tree is edited.
+
+Two pieces of the path are not module-level functions of ``src.fisher`` / ``src.laplace`` but live in
+modules that keep the rest of their contents: the Euler helper of ``src/utils.py`` and the threshold /
+metric methods of ``SSLAgent`` (``src/agent.py:357-455``).  Those are swapped in place -- at once when
+the module is already imported, otherwise by a post-import hook (a ``sys.meta_path`` finder that lets the
+normal import machinery load the module and patches it right after its body has run), so
+``patch_reference()`` works in the documented order: call it first, ``import train`` afterwards.
 """
 import importlib
+import importlib.abc
 import sys
 import types
 
@@ -30,10 +38,80 @@ def _package(name):
     return mod
 
 
+# ------------------------------------------------------------------ post-import hook
+class _PostImportPatcher(importlib.abc.MetaPathFinder):
+    """Runs ``callback(module)`` right after the import system has executed a watched module.
+
+    ``find_spec`` asks the finders behind it for the real spec and wraps that spec's loader, so the module is
+    found, loaded and cached exactly as without the hook; only the moment after ``exec_module`` is ours."""
+
+    def __init__(self):
+        self.callbacks = {}
+        self._busy = set()
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname not in self.callbacks or fullname in self._busy:
+            return None
+        self._busy.add(fullname)
+        try:
+            spec = None
+            for finder in sys.meta_path:
+                if finder is self:
+                    continue
+                find = getattr(finder, "find_spec", None)
+                spec = find(fullname, path, target) if find else None
+                if spec is not None:
+                    break
+        finally:
+            self._busy.discard(fullname)
+        if spec is None or spec.loader is None or not hasattr(spec.loader, "exec_module"):
+            return spec
+        loader, callback = spec.loader, self.callbacks[fullname]
+        run_body = loader.exec_module
+
+        def exec_module(module):
+            run_body(module)
+            callback(module)
+
+        try:
+            loader.exec_module = exec_module
+        except AttributeError:            # a loader without instance attributes: leave the import alone
+            return spec
+        return spec
+
+
+_HOOK = _PostImportPatcher()
+
+
+def _after_import(name, callback):
+    """Patch ``name`` now if it is imported, else when it is."""
+    mod = sys.modules.get(name)
+    if mod is not None:
+        callback(mod)
+        return "patched"
+    _HOOK.callbacks[name] = callback
+    if _HOOK not in sys.meta_path:
+        sys.meta_path.insert(0, _HOOK)
+    return "hooked"
+
+
+def _patch_utils_module(mod):
+    from . import utils as ours_utils
+    mod.compute_euler_angles_from_rotation_matrices = ours_utils.compute_euler_angles_from_rotation_matrices
+
+
+def _patch_agent_module(mod):
+    cls = getattr(mod, "SSLAgent", None)
+    if cls is not None:
+        patch_agent_class(cls)
+
+
 def patch_reference(patch_utils=True, patch_agent=True):
-    """Register the mirrors under the reference's module names; returns the list of
-    names that were patched.  Call before ``import train`` / ``from src.agent import ...``
-    (modules that already did ``from ... import name`` keep their old binding)."""
+    """Register the mirrors under the reference's module names and arrange for ``src.utils`` /
+    ``src.agent.SSLAgent`` to be patched (now, or as soon as they are imported).  Returns the list of names
+    handled, each as ``name`` (done) or ``name (on import)``.  Call it before ``import train`` /
+    ``from src.agent import ...``: modules that had ALREADY done ``from src.fisher.fisher_utils import name``
+    keep their old binding (Python semantics), which is why the call belongs at the top of the entry script."""
     done = []
     for ref_name, ours_name in _MIRRORS.items():
         ours = importlib.import_module(ours_name)
@@ -46,26 +124,35 @@ def patch_reference(patch_utils=True, patch_agent=True):
         done.append(ref_name)
     if patch_utils:
         # src/utils.py keeps its logging helpers; only the Euler function is swapped (src/utils.py:232)
-        from . import utils as ours_utils
-        ref_utils = sys.modules.get("src.utils")
-        if ref_utils is None:
-            try:
-                ref_utils = importlib.import_module("src.utils")
-            except Exception:
-                ref_utils = None
-        if ref_utils is not None:
-            ref_utils.compute_euler_angles_from_rotation_matrices = \
-                ours_utils.compute_euler_angles_from_rotation_matrices
-            done.append("src.utils.compute_euler_angles_from_rotation_matrices")
-    if patch_agent and "src.agent" in sys.modules:
-        patch_agent_class(sys.modules["src.agent"].SSLAgent)
-        done.append("src.agent.SSLAgent")
+        how = _after_import("src.utils", _patch_utils_module)
+        done.append("src.utils.compute_euler_angles_from_rotation_matrices" + ("" if how == "patched" else " (on import)"))
+    if patch_agent:
+        how = _after_import("src.agent", _patch_agent_module)
+        done.append("src.agent.SSLAgent" + ("" if how == "patched" else " (on import)"))
     return done
 
 
+def unpatch_reference():
+    """Remove the post-import hook and the injected module entries (tests; the swapped attributes of modules
+    that were already patched stay as they are)."""
+    if _HOOK in sys.meta_path:
+        sys.meta_path.remove(_HOOK)
+    _HOOK.callbacks.clear()
+    for ref_name, ours_name in _MIRRORS.items():
+        mod = sys.modules.get(ref_name)
+        if mod is not None and mod.__name__ == ours_name:
+            del sys.modules[ref_name]
+
+
 def patch_agent_class(cls):
-    """Bind the filter / metric slice of ``SSLAgent`` (src/agent.py:357-455) to the CUDA path."""
+    """Bind the filter / metric slice of ``SSLAgent`` (src/agent.py:357-455) to the CUDA path.  The reference's
+    own threshold method is kept as ``_reference_compute_dynamic_entropy_threshold``: the replacement hands
+    ``config.save_feat`` runs (backbone hooks + JSON feature dump, :366-401,409-414) back to it."""
     from . import agent as ours
+    if "_reference_compute_dynamic_entropy_threshold" not in vars(cls):
+        original = vars(cls).get("compute_dynamic_entropy_threshold")
+        if original is not None and original is not ours.compute_dynamic_entropy_threshold:
+            cls._reference_compute_dynamic_entropy_threshold = original
     cls.compute_dynamic_entropy_threshold = ours.compute_dynamic_entropy_threshold
     cls.compute_err_deg_from_matrices = staticmethod(ours.compute_err_deg_from_matrices)
     cls.compute_err_deg_from_quats = staticmethod(ours.compute_err_deg_from_quats)

@@ -22,19 +22,20 @@ def delta_R(N):
 
 class _LaplaceNLL(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, gt, grids):
+    def forward(ctx, pred, gt, grids, keep):
         need_grad = ctx.needs_input_grad[0]
         out = _ops.laplace_nll(pred, gt, grids, grad=need_grad, mode=True)
         if need_grad:
             ctx.save_for_backward(out["grad"])
         ctx.p_shape = pred.shape
+        ctx.keep = keep
         ctx.mark_non_differentiable(out["mode"])
         return out["nll"], out["mode"]
 
     @staticmethod
     def backward(ctx, g_nll, _g_mode):
         (grad,) = ctx.saved_tensors
-        return (grad * g_nll.reshape(-1, 1)).view(ctx.p_shape), None, None
+        return _ops.scale_rows(grad, g_nll, keep=ctx.keep).view(ctx.p_shape), None, None, None
 
 
 def analytical_mode(pred, fn_type="RLaplace"):
@@ -60,13 +61,20 @@ def log_pdf(fn_type, A, x, grids, broadcast=False):
     over_grid = (x.shape[0] == grids.shape[0]) or broadcast
     if fn_type == "RLaplace":
         if not over_grid:
-            return -_LaplaceNLL.apply(A, x, grids)[0]
-        logF = _ops.laplace_nll(A, A.new_zeros(A.shape) + torch.eye(3, device=A.device), grids,
-                                mode=False, logF=True)["logF"]
-        T = _signed_trace(A)
-        tr = torch.einsum("bij,nij->bn", A, x.reshape(-1, 3, 3))
-        power = -torch.sqrt(torch.clamp_min(T[:, None] - tr, EPS))
-        return -logF[:, None] + power - torch.log(-power)
+            return -_LaplaceNLL.apply(A, x, grids, None)[0]
+        # density over a whole grid (visualisation / checks, not the training path): logF and the signed trace
+        # come from the kernels, which do not record autograd history, so the result is returned WITHOUT a
+        # grad_fn rather than with a partial one (the reference is differentiable here; nothing in it uses that)
+        if A.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("log_pdf('RLaplace') over a grid / with broadcast=True is not differentiable here; "
+                                      "call it under torch.no_grad() (NLL_loss / the per-sample form are differentiable)")
+        with torch.no_grad():
+            logF = _ops.laplace_nll(A, A.new_zeros(A.shape) + torch.eye(3, device=A.device), grids,
+                                    mode=False, logF=True)["logF"]
+            T = _signed_trace(A)
+            tr = torch.einsum("bij,nij->bn", A, x.reshape(-1, 3, 3))
+            power = -torch.sqrt(torch.clamp_min(T[:, None] - tr, EPS))
+            return -logF[:, None] + power - torch.log(-power)
     if fn_type == "RFisher":
         tr_grid = torch.einsum("bij,nij->bn", A, grids.reshape(-1, 3, 3))
         c = tr_grid.max(dim=-1)[0]
@@ -77,11 +85,11 @@ def log_pdf(fn_type, A, x, grids, broadcast=False):
     raise KeyError(fn_type)
 
 
-def NLL_loss(fn_type, pred, gt, grids):
-    """(losses (b,), pred_orth (b,3,3))  -- rotation_laplace.py:24-34."""
+def NLL_loss(fn_type, pred, gt, grids, keep=None):
+    """(losses (b,), pred_orth (b,3,3))  -- rotation_laplace.py:24-34.  ``keep``: see fisher_utils.vmf_loss."""
     pred = pred.reshape(-1, 3, 3)
     if fn_type == "RLaplace":
-        return _LaplaceNLL.apply(pred, gt, grids)
+        return _LaplaceNLL.apply(pred, gt, grids, keep)
     losses = -log_pdf(fn_type, pred, gt, grids)
     pred_orth, _ = analytical_mode(pred, fn_type)
     return losses, pred_orth

@@ -10,10 +10,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "semiuhpe_b200.h")
+PROBE_HEADER = os.path.join(ROOT, "include", "semiuhpe_b200_probe.h")
 
 
-def declared_functions():
-    text = open(HEADER).read()
+def declared_functions(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     decls = re.findall(r"\b(suhpe_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", text)
     return {name: args for name, args in decls}
@@ -24,7 +25,11 @@ def test_header_symbols_are_exported(built):
     out = subprocess.run(["nm", "-D", "--defined-only", _build.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (suhpe_[a-z0-9_]+)", out))
     declared = set(declared_functions())
-    assert declared, "no declarations parsed"
+    probes = set(declared_functions(PROBE_HEADER))
+    assert declared and probes, "no declarations parsed"
+    assert not (declared & probes), "a measurement entry point leaked into the drop-in header"
+    assert "suhpe_fp32_probe" in probes and not any("probe" in name for name in declared)
+    declared |= probes
     assert declared == exported, f"header-only: {declared - exported}, library-only: {exported - declared}"
 
 
@@ -32,15 +37,23 @@ def test_ctypes_table_matches_header(built):
     from semiuhpe_b200 import _capi
     decl = declared_functions()
     assert set(_capi.SIGNATURES) == set(decl)
-    for name, args in decl.items():
-        n_args = 0 if args.strip() in ("", "void") else len(args.split(","))
-        assert len(_capi.SIGNATURES[name][1]) == n_args, name
+    probe_decl = declared_functions(PROBE_HEADER)
+    assert set(_capi.PROBE_SIGNATURES) == set(probe_decl)
+    for table, d in ((_capi.SIGNATURES, decl), (_capi.PROBE_SIGNATURES, probe_decl)):
+        for name, args in d.items():
+            n_args = 0 if args.strip() in ("", "void") else len(args.split(","))
+            assert len(table[name][1]) == n_args, name
     handle = _capi.lib()                      # dlopen works without a GPU
-    assert handle.suhpe_abi_version() == 1
+    assert handle.suhpe_abi_version() == _capi.ABI_VERSION == 2
+    assert not hasattr(handle, "suhpe_set_quadrature_cut_bits")     # no process-wide settings: cut_bits is per call
     assert handle.suhpe_error_string(0) == b"ok"
     assert handle.suhpe_error_string(_capi.EINVAL) == b"invalid argument"
     # argument validation happens before any CUDA call
-    assert handle.suhpe_fisher_fused_f32(None, None, 5, 1.0, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
+    assert handle.suhpe_fisher_fused_f32(None, None, 5, 1.0, 26, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
+    assert handle.suhpe_scale_rows_f32(None, 3, 9, None, None, None, None, None) == _capi.EINVAL
+    assert handle.suhpe_scale_rows_f32(None, 0, 9, None, None, None, None, None) == 0
+    assert handle.suhpe_ssl_step_f32(None, None, None, 1, None, None, 0, None, 0, None, 0.0, 1.0, 1.0, 0, 26,
+                                     None, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_entropy_threshold_f32(None, 0, 0, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_laplace_nll_f32(None, None, 1, None, 0, None, None, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_ema_update_f32(None, None, None, 3, 0.5, 0.5, 0, None) == _capi.EINVAL
@@ -51,7 +64,7 @@ def test_ctypes_table_matches_header(built):
 def test_header_is_plain_c(tmp_path):
     """The boundary is a C ABI: the header must compile as C99 (and as C++) on its own, warning-free."""
     src = tmp_path / "use_header.c"
-    src.write_text('#include "semiuhpe_b200.h"\nint main(void) { return suhpe_abi_version() < 0; }\n')
+    src.write_text('#include "semiuhpe_b200.h"\n#include "semiuhpe_b200_probe.h"\nint main(void) { return suhpe_abi_version() < 0; }\n')
     inc = os.path.join(ROOT, "include")
     for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
                 ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)]):
@@ -68,7 +81,7 @@ def test_c_host_links_and_calls_the_library(built, tmp_path):
         '#include <stdio.h>\n#include "semiuhpe_b200.h"\n'
         'int main(void) {\n'
         '  printf("%d|%s|%s|", suhpe_abi_version(), suhpe_error_string(0), suhpe_error_string(SUHPE_EINVAL));\n'
-        '  printf("%d|", suhpe_fisher_fused_f32(NULL, NULL, 4, 1.0f, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL) == SUHPE_EINVAL);\n'
+        '  printf("%d|", suhpe_fisher_fused_f32(NULL, NULL, 4, 1.0f, SUHPE_CUT_BITS_DEFAULT, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL) == SUHPE_EINVAL);\n'
         '  printf("%d\\n", suhpe_ema_update_f32(NULL, NULL, NULL, 0, 0.5f, 0.5f, 1, NULL));\n'
         '  return 0;\n}\n')
     exe = tmp_path / "host"
@@ -76,7 +89,7 @@ def test_c_host_links_and_calls_the_library(built, tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L", lib_dir, "-lsemiuhpe_b200", f"-Wl,-rpath,{lib_dir}"], check=True, capture_output=True, text=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
-    assert out == "1|ok|invalid argument|1|0", out
+    assert out == "2|ok|invalid argument|1|0", out
 
 
 def test_sass_is_sm100a_only(built):

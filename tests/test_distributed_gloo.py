@@ -110,3 +110,52 @@ def test_single_process_path_without_process_group(golden):
     pool = golden("select")["entropy"]
     got = global_entropy_threshold(None, 0.95, backend=NumpyHistogramBackend(pool))
     assert got == float(np.sort(pool)[int(len(pool) * 0.95)])
+
+
+def _mean_worker(rank, world, port, values, weights, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semiuhpe_b200.distributed import sharded_mean
+    bounds = np.linspace(0, len(values), world + 1).astype(int)
+    bounds[1:-1] += 3                                        # ragged shards
+    lo, hi = bounds[rank], bounds[rank + 1]
+    v = torch.from_numpy(values[lo:hi].copy()).requires_grad_(True)
+    w = torch.from_numpy(weights[lo:hi].copy())
+    plain = sharded_mean(v)
+    masked = sharded_mean(v, weights=w)
+    (plain + 2 * masked).backward()
+    out[rank] = (float(plain), float(masked), v.grad.numpy().copy(), lo, hi)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_mean_equals_single_process_mean(world):
+    """losses.mean() (src/agent.py:83) and the masked unsupervised mean x mask ratio (:163-166) over a batch that is
+    sharded across ranks: the value every rank gets and the gradient its slice gets are the single-process ones."""
+    rng = np.random.default_rng(5)
+    n = 1000
+    values = rng.normal(size=n).astype(np.float32) * 7
+    weights = (rng.random(n) < 0.8).astype(np.float32)
+    values[weights == 0] = np.nan                            # filtered rows may hold anything (0 * NaN must not form)
+    out = mp.Manager().dict()
+    mp.spawn(_mean_worker, args=(world, _free_port(), values, weights, out), nprocs=world, join=True)
+    kept = weights != 0
+    want_masked = float(values[kept].astype(np.float64).sum() / n)
+    ref = torch.from_numpy(np.where(kept, values, 0).astype(np.float32)).requires_grad_(True)
+    for rank in range(world):
+        plain, masked, grad, lo, hi = out[rank]
+        assert np.isnan(plain)                               # the plain mean of a pool with NaN rows is NaN, as in torch
+        assert abs(masked - want_masked) <= 1e-6 * abs(want_masked)
+        assert np.allclose(grad[kept[lo:hi]], 1.0 / n + 2.0 / n, rtol=1e-6)
+        assert masked == out[0][1]                           # bit-identical on every rank
+    # without NaN rows the plain mean is the global mean
+    values2 = np.where(kept, values, 1.5).astype(np.float32)
+    out2 = mp.Manager().dict()
+    mp.spawn(_mean_worker, args=(world, _free_port(), values2, weights, out2), nprocs=world, join=True)
+    for rank in range(world):
+        assert abs(out2[rank][0] - float(values2.astype(np.float64).mean())) <= 1e-6
+        assert out2[rank][0] == out2[0][0]
