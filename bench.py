@@ -195,6 +195,14 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    cores = None
+    if world > 1 and not args.no_pin:
+        # one disjoint slice of the host cores per rank, set BEFORE any pinned buffer is allocated (first-touch
+        # placement follows the cores): the ranks' copy threads and Python threads stop migrating over each other
+        avail = sorted(os.sched_getaffinity(0))
+        per = max(len(avail) // world, 1)
+        cores = avail[(local * per) % len(avail):(local * per) % len(avail) + per] or avail
+        os.sched_setaffinity(0, cores)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -316,7 +324,7 @@ def run_ours(args):
     check_dev = threshold_check(torch, dist, dev, world, rank, ent, thr, kept_n, k)
 
     # end-to-end leg on every rank at once (they share the host's PCIe/memory system), max over ranks
-    e2e = None if args.no_e2e else run_e2e(torch, dist, dev, n, args, world, rank, k)
+    e2e = None if args.no_e2e else run_e2e(torch, dist, dev, n, args, world, rank, k, cores)
 
     if rank != 0:
         if world > 1:
@@ -441,7 +449,7 @@ def threshold_check(torch, dist, dev, world, rank, ent, thr, kept_local, k):
     return out
 
 
-def run_e2e(torch, dist, dev, n, args, world, rank, k):
+def run_e2e(torch, dist, dev, n, args, world, rank, k, cores=None):
     """Same step through the C ABI's host-buffer entry: pinned host A/R -> H2D -> K2/K3 -> D2H."""
     from semiuhpe_b200.host_pipeline import FisherFilterPipeline
     gen = torch.Generator().manual_seed(77 + rank)
@@ -490,6 +498,7 @@ def run_e2e(torch, dist, dev, n, args, world, rank, k):
                    + ("suhpe_fisher_pool_host + all-gathered radix select + mask" if world > 1 else "suhpe_fisher_filter_host")
                    + f" ({args.e2e_chunk}-pair chunks, H2D / kernel / D2H queues over 4 buffers)"),
            "threshold": res["threshold"], "kept": res["kept"],
+           "host_cores_per_rank": None if cores is None else len(cores),
            "note": "all ranks concurrently (they share the host's PCIe/memory system), max over ranks; global threshold"
                    if world > 1 else "single GPU"}
     if link:
@@ -716,6 +725,7 @@ def main():
     ap.add_argument("--skip-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not restrict each rank to its own slice of the host cores")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

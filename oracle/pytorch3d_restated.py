@@ -16,7 +16,13 @@ Published behaviour restated here
 ``so3_relative_angle(R1, R2)``: ``c = (trace(R1 R2^T) - 1) / 2``; a trace
 outside ``[-1-eps, 3+eps]`` (eps=1e-4) raises ``ValueError``; the angle is
 ``acos(c)`` for ``|c| < 1-1e-4`` and the first-order Taylor extension of acos
-about ``+-(1-1e-4)`` outside (so identical rotations give 0.01414 rad... not 0).
+about ``+-(1-1e-4)`` outside, ``acos(b) + (x - b) * (-1/sqrt(1 - b^2))`` -- so identical rotations give
+``acos(1-1e-4) - 1e-4/sqrt(1-(1-1e-4)^2)`` = 0.0141422 - 0.0070711 = **0.0070711 rad = 0.40514 deg**, not 0.
+
+Known answers derived from these formulas in plain float64 (``tests/golden/make_pytorch3d_kat.py`` ->
+``tests/golden/pytorch3d_kat.json``, independent of this file) are checked in ``tests/test_oracle_golden.py``;
+they pin the restatement to the documented algorithm, not to pytorch3d's own output -- the row stays
+"parity unpinned" until a real pytorch3d result has been compared.
 """
 import math
 

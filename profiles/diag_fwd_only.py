@@ -9,10 +9,9 @@ scales = torch.tensor([0.3, 1.0, 3.0, 5.0, 10.0, 20.0]).repeat_interleave(1000)
 A = (torch.randn(len(scales), 9, generator=gen) * scales[:, None]).to(dev)
 for n in (6000, 200000):
     a = A if n == 6000 else (10 * torch.randn(n, 9, generator=gen)).to(dev)
-    full = _ops.fisher_fused(a, None, 1.0, nll=True, entropy=True)["nll"]
-    fwd = _ops.fisher_fused(a, None, 1.0, nll=True)["nll"]
-    full2 = _ops.fisher_fused(a, None, 1.0, nll=True, entropy=True)["nll"]
-    d = (full - fwd).abs()
-    bad = (full != fwd)
-    print(f"n={n}: full-vs-fwd mismatches {int(bad.sum())} max|d|={d.max().item():.3e} rel={(d / full.abs().clamp(min=1e-3)).max().item():.3e}; "
-          f"full rerun identical: {bool(torch.equal(full, full2))}; first bad idx {bad.nonzero().flatten()[:8].tolist()}")
+    for bits in (26, 0):
+        full = _ops.fisher_fused(a, None, 1.0, nll=True, entropy=True, S=True, logC=True, cut_bits=bits)
+        fwd = _ops.fisher_fused(a, None, 1.0, nll=True, S=True, logC=True, cut_bits=bits)
+        bad = (full["nll"] != fwd["nll"])
+        print(f"n={n} bits={bits}: nll mismatches {int(bad.sum())}  S mismatches {int((full['S'] != fwd['S']).any(1).sum())}  "
+              f"logC mismatches {int((full['logC'] != fwd['logC']).sum())}  max|d nll|={(full['nll'] - fwd['nll']).abs().max().item():.3e}")

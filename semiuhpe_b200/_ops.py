@@ -142,9 +142,11 @@ def scale_rows(rows, row_weight=None, scalar_weight=None, keep=None):
     w = None
     if row_weight is not None:
         w = row_weight.detach().reshape(-1)
-        if w.numel() == 1:
-            scalar_weight, w = (w if scalar_weight is None else scalar_weight * w), None
+        if w.numel() == 1 and scalar_weight is None and n != 1:
+            scalar_weight, w = w, None                  # a broadcast scalar (e.g. the gradient of a .sum())
         else:
+            if w.numel() == 1:
+                w = w.expand(n)
             if w.numel() != n:
                 raise RuntimeError(f"scale_rows: {w.numel()} weights for {n} rows")
             w = w.to(torch.float32)

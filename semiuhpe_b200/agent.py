@@ -313,6 +313,9 @@ def compute_err_deg_from_matrices(pred, gt, gt_euler=None):
     geodesic angle via pytorch3d's ``so3_relative_angle`` semantics when ``gt_euler`` is
     None, else the mean absolute (pitch,yaw,roll) error."""
     if gt_euler is None:
+        if torch.compiler.is_compiling():
+            from . import torch_ops  # noqa: F401
+            return torch.ops.semiuhpe_b200.geodesic_deg(pred, gt)
         return _ops.so3_metrics(pred, gt, geo=True)["geo"]
     return _ops.so3_metrics(pred, gt, gt_euler, full_range=False, mae=True)["mae"]
 

@@ -41,9 +41,7 @@ namespace {
 #ifndef SUHPE_K2_RR
 #define SUHPE_K2_RR 1
 #endif
-#ifndef SUHPE_K2_BFLY
-#define SUHPE_K2_BFLY 1
-#endif
+
 constexpr int kWarpsPerBlock = SUHPE_K2_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -492,19 +490,12 @@ fisher_fused_kernel(FisherArgs p) {
                 else if (f == 1) pN1 = Y - UY;
                 else pN2 = Y - UY;
             }
-            if (!SUHPE_K2_BFLY) {
-                pY0 = warp_sum(pY0); pUY0 = warp_sum(pUY0); pN1 = warp_sum(pN1); pN2 = warp_sum(pN2);
-                if (lane == j) {                  // F, UY - c, N1, N2: sums minus this sample's corrections
-                    float* mine9 = ws.a + lane * 9;
-                    mine9[4] = pY0 - mine9[4]; mine9[5] = pUY0 - mine9[5]; mine9[6] = pN1 - mine9[6]; mine9[7] = pN2 - mine9[7];
-                }
-            } else if (NFAM == 1) {
-                pY0 = warp_sum(pY0);
-                if (lane == j) { float* mine9 = ws.a + lane * 9; mine9[4] = pY0 - mine9[4]; }
-            } else {
+            {
                 // Four warp sums in one butterfly: after the exchanges over lane bits 4 and 3 every lane carries
                 // ONE of the four quantities (index 2*bit4 + bit3), so 6 shuffles do the work of 20.  Lanes
                 // 0, 8, 16, 24 end up with the totals of F, UY, N1, N2 and subtract the sample's corrections in place.
+                // (The forward-only instantiation runs the same sequence with three zeros: its F -- hence its NLL --
+                // is then bit-identical to the full launch's, which a plain 5-step shuffle sum was not on the device.)
                 const bool b4 = (lane_r & 16) != 0, b3 = (lane_r & 8) != 0;
                 float k0 = b4 ? pN1 : pY0, k1 = b4 ? pN2 : pUY0;
                 const float s0 = b4 ? pY0 : pN1, s1 = b4 ? pUY0 : pN2;

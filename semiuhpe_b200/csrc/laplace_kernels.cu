@@ -29,7 +29,7 @@ namespace suhpe {
 namespace {
 
 #ifndef SUHPE_K2L_NEWTON
-#define SUHPE_K2L_NEWTON 1
+#define SUHPE_K2L_NEWTON 0      // 1 = one Newton step on MUFU.RSQ's square root (the round-1 kernel: +3 packed ops per pair)
 #endif
 constexpr int kLapThreads = 256;
 constexpr int kGridChunk = 4608;           // grid points resident in shared memory at once

@@ -41,17 +41,32 @@ class _FisherNLL(torch.autograd.Function):
         return _ops.scale_rows(grad, g_nll, keep=ctx.keep).view(ctx.a_shape), None, None, None, None
 
 
+def _compiling():
+    return torch.compiler.is_compiling()
+
+
+def _wants_grad(t):
+    return bool(t.requires_grad and torch.is_grad_enabled())
+
+
 def vmf_loss(net_out, R, overreg=1.05, keep=None):
     """(loss (b,), Rest (b,3,3))  -- reference fisher_utils.py:14-18.
     ``keep`` (extension, optional, (b,) bool): rows a mask filtered out; their gradient is exactly zero whatever
     the row holds (the reference gathers ``pred[mask]`` before the loss: src/agent.py:157)."""
     A = net_out.view(-1, 3, 3)
+    if _compiling():                                   # traced / compiled step: the registered dispatcher op
+        from .. import torch_ops  # noqa: F401
+        loss_v, Rest, _ = torch.ops.semiuhpe_b200.fisher_nll(A, R, float(overreg), True, _wants_grad(A), keep)
+        return loss_v, Rest.detach()                   # the projected rotation carries no gradient (as in eager mode)
     loss_v, Rest = _FisherNLL.apply(A, R, float(overreg), True, keep)
     return loss_v, Rest
 
 
 def KL_Fisher(A, R, overreg=1.05):
     """Matrix-Fisher NLL (b,) -- reference fisher_utils.py:21-36."""
+    if _compiling():
+        from .. import torch_ops  # noqa: F401
+        return torch.ops.semiuhpe_b200.fisher_nll(A, R, float(overreg), False, _wants_grad(A), None)[0]
     loss_v, _ = _FisherNLL.apply(A, R, float(overreg), False, None)
     return loss_v
 
@@ -59,6 +74,9 @@ def KL_Fisher(A, R, overreg=1.05):
 def batch_torch_A_to_R(A):
     """Proper-SVD projection onto SO(3), (b,9)|(b,3,3) -> (b,3,3)
     -- reference fisher_utils.py:39-48."""
+    if _compiling():
+        from .. import torch_ops  # noqa: F401
+        return torch.ops.semiuhpe_b200.proper_rotation(A)
     return _ops.proper_svd(A, rot=True, what="batch_torch_A_to_R")["rot"]
 
 
@@ -71,6 +89,9 @@ def fisher_entropy(A):
     """(b,9)|(b,3,3) -> (b,) entropy of the matrix-Fisher distribution
     -- reference fisher_utils.py:70-81 (Fisher -> Bingham -> autograd chain, collapsed
     to H = log f(s) + sum_j s_j (1 - g_j))."""
+    if _compiling():
+        from .. import torch_ops  # noqa: F401
+        return torch.ops.semiuhpe_b200.fisher_entropy(A)
     return _ops.fisher_fused(A, None, 1.0, entropy=True, what="fisher_entropy")["entropy"]
 
 
@@ -117,4 +138,7 @@ def fisher_CE(A1, A2, target_G=None, keep=None):
     if isinstance(A1, torch.Tensor) and A1.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError("fisher_CE: the gradient w.r.t. the target A1 is not implemented "
                                   "(the reference's training loop detaches it, src/agent.py:107)")
+    if _compiling():
+        from .. import torch_ops  # noqa: F401
+        return torch.ops.semiuhpe_b200.fisher_ce(A1, A2, _wants_grad(A2), target_G, keep)[0]
     return _FisherCE.apply(A1, A2, target_G, keep)

@@ -89,6 +89,10 @@ def NLL_loss(fn_type, pred, gt, grids, keep=None):
     """(losses (b,), pred_orth (b,3,3))  -- rotation_laplace.py:24-34.  ``keep``: see fisher_utils.vmf_loss."""
     pred = pred.reshape(-1, 3, 3)
     if fn_type == "RLaplace":
+        if torch.compiler.is_compiling():               # traced / compiled step: the registered dispatcher op
+            from .. import torch_ops  # noqa: F401
+            nll, mode, _ = torch.ops.semiuhpe_b200.laplace_nll(pred, gt, grids, bool(pred.requires_grad and torch.is_grad_enabled()), keep)
+            return nll, mode.detach()
         return _LaplaceNLL.apply(pred, gt, grids, keep)
     losses = -log_pdf(fn_type, pred, gt, grids)
     pred_orth, _ = analytical_mode(pred, fn_type)

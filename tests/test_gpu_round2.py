@@ -131,7 +131,7 @@ def test_filtered_nan_rows_never_reach_the_gradient(cuda):
     good = S.to(cuda).requires_grad_(True)
     fisher_CE(W.to(cuda), good, keep=keep.to(cuda)).sum().backward()
     assert torch.equal(good.grad.cpu()[keep], g[keep])
-    with pytest.raises(AssertionError):                           # an UNfiltered NaN row still asserts like the reference
+    with pytest.raises(torch.linalg.LinAlgError):                 # an UNfiltered NaN row still raises like the reference's torch.svd
         fisher_CE(W.to(cuda), S_bad.to(cuda))
     # the sync-free step: a teacher row with NaN is filtered by its own NaN entropy (NaN < thr is false)
     semiuhpe_b200.set_error_checking(False)

@@ -149,6 +149,46 @@ def test_pytorch3d_restatement_is_consistent():
     assert torch.allclose(ang, torch.full_like(ang, 0.0070711), atol=5e-5)
 
 
+def _kat():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pytorch3d_kat.json")) as f:
+        return json.load(f)
+
+
+def test_pytorch3d_restatement_against_formula_derived_known_answers():
+    """a16 stays PARITY UNPINNED (no pytorch3d output was ever compared); the known answers here come from the
+    published formulas evaluated independently in float64 (tests/golden/make_pytorch3d_kat.py): the acos
+    extension at and beyond +-(1-1e-4), the 0.0070711 rad identity, the trace check, the four
+    matrix_to_quaternion branches and non-unit quaternions."""
+    kat = _kat()
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+        x = torch.tensor([r["x"] for r in kat["acos_linear_extrapolation"]], dtype=dtype)
+        y = torch.tensor([r["y"] for r in kat["acos_linear_extrapolation"]], dtype=dtype)
+        got = p3d.acos_linear_extrapolation(x)
+        # fp32: acos next to the bound amplifies the rounding of x by 1/sqrt(1-x^2) ~ 70
+        assert (got - y).abs().max() < (tol if dtype == torch.float64 else 2e-5)
+        rows = kat["so3_relative_angle_about_z"]
+        R1 = torch.tensor([r["R1"] for r in rows], dtype=dtype)
+        I = torch.eye(3, dtype=dtype).expand(len(rows), 3, 3)
+        want = torch.tensor([r["angle"] for r in rows], dtype=dtype)
+        assert (p3d.so3_relative_angle(R1, I) - want).abs().max() < (1e-9 if dtype == torch.float64 else 5e-4)
+        for r in kat["matrix_to_quaternion"]:
+            q = p3d.matrix_to_quaternion(torch.tensor(r["M"], dtype=dtype)[None])[0]
+            assert (q - torch.tensor(r["q"], dtype=dtype)).abs().max() < max(tol, 1e-6), r["branch"]
+        for r in kat["quaternion_to_matrix"]:
+            M = p3d.quaternion_to_matrix(torch.tensor(r["q"], dtype=dtype)[None])[0]
+            assert (M - torch.tensor(r["M"], dtype=dtype)).abs().max() < max(tol, 1e-6)
+    assert abs(kat["identity_angle_rad"] - 0.0070711) < 1e-7 and abs(kat["identity_angle_deg"] - 0.40514) < 1e-5
+    eye = torch.eye(3, dtype=torch.float64)[None]
+    assert abs(p3d.so3_relative_angle(eye, eye).item() - kat["identity_angle_rad"]) < 1e-12
+    for M in kat["trace_out_of_range"]:
+        with pytest.raises(ValueError):
+            p3d.so3_relative_angle(torch.tensor(M, dtype=torch.float64)[None], eye)
+    for M in kat["trace_in_range_edge"]:
+        p3d.so3_relative_angle(torch.tensor(M, dtype=torch.float64)[None], eye)
+
+
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
 def test_oracle_matches_live_reference():
     ref = ref_shim.load()
