@@ -35,6 +35,21 @@ def get_6DRepNet_Rot(x, y, z):
     return Rz.dot(Ry.dot(Rx))
 
 
+def rot_euler_6DRepNet(rotation_matrices, full_range=False):
+    """One 3x3 matrix -> numpy (pitch, yaw, roll) radians: the per-sample host twin of
+    :func:`compute_euler_angles_from_rotation_matrices` that the datasets use to build labels
+    (src/utils.py:263-286).  The singular flag (``sy < 1e-6``) is taken BEFORE the full-range sign flip, as there."""
+    R = np.asarray(rotation_matrices)
+    sy = np.sqrt(R[0, 0] * R[0, 0] + R[1, 0] * R[1, 0])
+    singular = bool(sy < 1e-6)
+    if full_range and R[0, 0] < 0:
+        sy = -sy
+    yaw = math.atan2(-R[2, 0], sy)
+    if singular:
+        return np.array([math.atan2(-R[1, 2], R[1, 1]), yaw, 0.0])
+    return np.array([math.atan2(R[2, 1], R[2, 2]), yaw, math.atan2(R[1, 0], R[0, 0])])
+
+
 def limit_angle(angle, pi=180.0):
     """Wrap degrees into [-180, 180] (host scalar helper, src/utils.py:289-300)."""
     if angle < -pi:

@@ -149,3 +149,14 @@ def test_host_helpers_match_oracle(golden):
     g = golden("metrics")
     assert [utils.limit_angle(a) for a in g["limit_in"]] == list(g["limit_out"])
     np.testing.assert_allclose(utils.get_6DRepNet_Rot(0.3, -0.2, 1.1), orc.rot_from_euler(0.3, -0.2, 1.1), atol=1e-15)
+    # rot_euler_6DRepNet (src/utils.py:263-286): the per-sample numpy twin of the batched Euler function
+    import torch
+    rng = np.random.default_rng(3)
+    for full_range in (False, True):
+        for _ in range(50):
+            p, y, r = rng.uniform(-np.pi, np.pi, 3) * np.array([0.49, 0.99 if full_range else 0.49, 0.99])
+            R = utils.get_6DRepNet_Rot(p, y, r)
+            want = orc.euler_from_matrices(torch.from_numpy(R)[None], full_range=full_range)[0].numpy()
+            np.testing.assert_allclose(utils.rot_euler_6DRepNet(R, full_range), want, atol=1e-12)
+    Rs = np.array([[0.0, 0.0, 1.0], [0.0, 1.0, 0.0], [-1.0, 0.0, 0.0]])       # gimbal lock: sy = 0
+    np.testing.assert_allclose(utils.rot_euler_6DRepNet(Rs), [0.0, np.pi / 2, 0.0], atol=1e-12)

@@ -396,3 +396,33 @@ def test_global_threshold_over_nccl_matches_sort_of_the_concatenated_pool(cuda):
     mp.spawn(_nccl_worker, args=(2, port, 1 << 18, 0.95, ret), nprocs=2, join=True)
     assert len(ret) == 2 and all(v[0] for v in ret.values()), dict(ret)
     assert ret[0][1] == ret[1][1]
+
+
+def test_err_deg_from_quats_and_formula_known_answers(cuda):
+    """src/agent.py:420-424 (real-first quaternions -> geodesic degrees) against the oracle, and K4's geodesic angle
+    against the formula-derived known answers of tests/golden/pytorch3d_kat.json (acos extension at +-(1-1e-4), the
+    0.40514 deg identity, the trace check).  a16 stays parity-unpinned: these are not pytorch3d outputs."""
+    import json
+    from oracle import pytorch3d_restated as p3d, so3_oracle as orc
+    from semiuhpe_b200.agent import compute_err_deg_from_quats, compute_err_deg_from_matrices
+    gen = torch.Generator().manual_seed(13)
+    q1 = torch.randn(500, 4, generator=gen)
+    q2 = torch.randn(500, 4, generator=gen) * 3.0                     # non-unit: two_s = 2/|q|^2 handles it
+    want = orc.geodesic_deg(p3d.quaternion_to_matrix(q1), p3d.quaternion_to_matrix(q2))
+    got = compute_err_deg_from_quats(q1.to(cuda), q2.to(cuda)).cpu()
+    assert torch.allclose(got, want, rtol=1e-4, atol=2e-3)
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pytorch3d_kat.json")) as f:
+        kat = json.load(f)
+    rows = kat["so3_relative_angle_about_z"]
+    R1 = torch.tensor([r["R1"] for r in rows], dtype=torch.float32).to(cuda)
+    I = torch.eye(3).expand(len(rows), 3, 3).contiguous().to(cuda)
+    deg = compute_err_deg_from_matrices(R1, I).cpu().double()
+    want = torch.tensor([np.degrees(r["angle"]) for r in rows])
+    # fp32 next to the bound: d acos/dx ~ 70, x carries ~6e-8 of rounding -> ~3e-4 deg
+    assert (deg - want).abs().max() < 2e-3, (deg - want).abs().max()
+    assert abs(float(deg[0]) - kat["identity_angle_deg"]) < 1e-4
+    for M in kat["trace_out_of_range"]:
+        with pytest.raises(ValueError):
+            compute_err_deg_from_matrices(torch.tensor(M, dtype=torch.float32)[None].to(cuda), torch.eye(3)[None].to(cuda))
+    for M in kat["trace_in_range_edge"]:
+        compute_err_deg_from_matrices(torch.tensor(M, dtype=torch.float32)[None].to(cuda), torch.eye(3)[None].to(cuda))
