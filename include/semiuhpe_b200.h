@@ -48,6 +48,11 @@ const char* suhpe_error_string(int code);
  * (src/fisher/between_bingham_fisher.py:63-82).  R,S,U,V,status nullable. */
 int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U, float* V,
                          int* status, void* stream);
+/* Backward of R = U V^T w.r.t. A (batch_torch_A_to_R is differentiable through torch.svd in the reference,
+ * src/fisher/fisher_utils.py:39-48): gradA = U Q V^T, Q_ij = (P_ij - P_ji) / (S_i + S_j), P = U^T gradR V,
+ * with U, V, S exactly as suhpe_proper_svd_f32 wrote them.  S_i + S_j = 0 contributes nothing. */
+int suhpe_proper_svd_backward_f32(const float* U, const float* V, const float* S, const float* gradR, int64_t n,
+                                  float* gradA, void* stream);
 
 /* K2 -- fused matrix-Fisher head: per sample
  *   nll     = -<A,Rgt> + overreg * logC(S)                 KL_Fisher   fisher_utils.py:21-36

@@ -22,6 +22,7 @@ SIGNATURES = {
     "suhpe_abi_version": (ctypes.c_int, []),
     "suhpe_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "suhpe_proper_svd_f32": (ctypes.c_int, [c_vp, i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "suhpe_proper_svd_backward_f32": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, i64, c_vp, c_vp]),
     "suhpe_fisher_fused_f32": (ctypes.c_int, [c_vp, c_vp, i64, f32, i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_fisher_from_s_f32": (ctypes.c_int, [c_vp, i64, i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_fisher_ce_f32": (ctypes.c_int, [c_vp, c_vp, i64, i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

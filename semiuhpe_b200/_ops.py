@@ -240,6 +240,19 @@ def proper_svd(A, *, rot=True, S=False, U=False, V=False, what="svd"):
     return out
 
 
+def proper_svd_backward(U, V, S, grad_R):
+    """d L / d A (n,9) from d L / d R for R = U V^T of the proper SVD (K1's U, V, S)."""
+    U9, V9, G9 = as_records(U, "U"), as_records(V, "V"), as_records(grad_R, "grad_R")
+    S3 = as_records(S, "S", 3)
+    n = U9.shape[0]
+    out = torch.empty((n, 9), dtype=torch.float32, device=U9.device)
+    if n:
+        with on_device(U9.device) as idx:
+            check(lib().suhpe_proper_svd_backward_f32(ptr(U9), ptr(V9), ptr(S3), ptr(G9), n, ptr(out), stream(idx)),
+                  "proper_svd_backward")
+    return out
+
+
 def laplace_nll(A, R, grids, *, grad=False, mode=True, logF=False):
     """K2L."""
     A9 = as_records(A, "pred")

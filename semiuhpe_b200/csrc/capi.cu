@@ -216,6 +216,12 @@ int suhpe_proper_svd_f32(const float* A, int64_t n, float* R, float* S, float* U
     return rc(launch_proper_svd(p, st(stream)));
 }
 
+int suhpe_proper_svd_backward_f32(const float* U, const float* V, const float* S, const float* gradR, int64_t n,
+                                  float* gradA, void* stream) {
+    if (n < 0 || (n > 0 && (!U || !V || !S || !gradR || !gradA))) return SUHPE_EINVAL;
+    return rc(launch_polar_backward(U, V, S, gradR, (long long)n, gradA, st(stream)));
+}
+
 int suhpe_fisher_fused_f32(const float* A, const float* Rgt, int64_t n, float overreg, int32_t cut_bits,
                            float* nll, float* grad, float* Rout, float* entropy, float* logC,
                            float* S, float* G, uint64_t* hist, int* status, void* stream) {

@@ -630,6 +630,54 @@ proper_svd_kernel(SvdArgs p) {
 }
 
 // ---------------------------------------------------------------------------
+// Backward of K1's rotation output (batch_torch_A_to_R is differentiable in the reference through torch.svd:
+// src/fisher/fisher_utils.py:39-48).  With A = U diag(s) V^T (proper: det U = det V = +1, s3 signed) the polar
+// factor R = U V^T moves by  U^T dR V = X,  X_ij = (M_ij - M_ji) / (s_i + s_j),  M = U^T dA V,  so for an incoming
+// G = dL/dR:   dL/dA = U Q V^T,   Q_ij = (P_ij - P_ji) / (s_i + s_j),   P = U^T G V   (Q_ii = 0).
+// s_i + s_j = 0 (a reflection-degenerate spectrum, where the projection itself is not unique) contributes nothing.
+// Thread per matrix; 144 B in, 36 B out per matrix: HBM-bound and tiny.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSvdThreads)
+polar_backward_kernel(const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ S,
+                      const float* __restrict__ G, long long n, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * kSvdThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kSvdThreads) {
+        float u[9], v[9], g[9], s[3], t[9], p[9], q[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { u[k] = __ldg(U + i * 9 + k); v[k] = __ldg(V + i * 9 + k); g[k] = __ldg(G + i * 9 + k); }
+        s[0] = __ldg(S + i * 3); s[1] = __ldg(S + i * 3 + 1); s[2] = __ldg(S + i * 3 + 2);
+        // t = G V, p = U^T t
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                t[3 * r + c] = fmaf(g[3 * r], v[c], fmaf(g[3 * r + 1], v[3 + c], g[3 * r + 2] * v[6 + c]));
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                p[3 * r + c] = fmaf(u[r], t[c], fmaf(u[3 + r], t[3 + c], u[6 + r] * t[6 + c]));
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float den = s[r] + s[c];
+                q[3 * r + c] = (r == c || den == 0.0f) ? 0.0f : div_rn(p[3 * r + c] - p[3 * c + r], den);
+            }
+        // out = U q V^T
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                t[3 * r + c] = fmaf(u[3 * r], q[c], fmaf(u[3 * r + 1], q[3 + c], u[3 * r + 2] * q[6 + c]));
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                out[i * 9 + 3 * r + c] = fmaf(t[3 * r], v[3 * c], fmaf(t[3 * r + 1], v[3 * c + 1], t[3 * r + 2] * v[3 * c + 2]));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // fisher_CE closing kernel: thread per pair.  The two quadratures (target and
 // prediction) are K2 launches; this step re-derives both proper SVDs (registers, same routine),
 // builds the two quaternion frames and evaluates fisher_ce_close (so3_math.cuh).  HBM-bound:
@@ -912,6 +960,16 @@ cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream) {
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec_ok = aligned(p.A1) && aligned(p.A2) && aligned(p.grad);
     fisher_ce_close_kernel<<<(unsigned)blocks, kSvdThreads, 0, stream>>>(p, vec_ok);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_polar_backward(const float* U, const float* V, const float* S, const float* G, long long n, float* out,
+                                  cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + kSvdThreads - 1) / kSvdThreads;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    polar_backward_kernel<<<(unsigned)blocks, kSvdThreads, 0, stream>>>(U, V, S, G, n, out);
     return cudaGetLastError();
 }
 

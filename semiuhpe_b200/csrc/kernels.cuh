@@ -106,6 +106,9 @@ inline cudaError_t allow_dynamic_smem(K kernel, size_t bytes, unsigned long long
 cudaError_t launch_fisher_fused(FisherArgs p, cudaStream_t stream);
 cudaError_t launch_fisher_ce_close(FisherCeArgs p, cudaStream_t stream);
 cudaError_t launch_proper_svd(SvdArgs p, cudaStream_t stream);
+// d L / d A from G = d L / d R for R = U V^T of the proper SVD (U, V, S as K1 wrote them)
+cudaError_t launch_polar_backward(const float* U, const float* V, const float* S, const float* G, long long n, float* out,
+                                  cudaStream_t stream);
 // out[i,:] = in[i,:] * row_weight[i] * *scalar_weight, zero rows where keep[i] == 0 (each factor nullable)
 cudaError_t launch_scale_rows(const float* in, long long n, int width, const float* row_weight, const float* scalar_weight,
                               const uint8_t* keep, float* out, cudaStream_t stream);

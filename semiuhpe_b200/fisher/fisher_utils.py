@@ -5,8 +5,8 @@ Same names, arguments and return shapes; every function is ONE kernel launch
 reference's CPU SVD round trips and hundreds of elementwise ops.  Differences that are deliberate:
 
 * inputs must be CUDA fp32 (the reference moves them to the CPU itself);
-* ``fisher_entropy`` / ``batch_torch_A_to_R`` return plain tensors without a
-  ``grad_fn`` (the agent uses them detached: src/agent.py:108,139,152);
+* ``fisher_entropy`` returns a plain tensor without a ``grad_fn`` (the agent uses it detached:
+  src/agent.py:108,139); ``batch_torch_A_to_R`` is differentiable when its input requires a gradient;
 * ``vmf_loss`` / ``KL_Fisher`` / ``fisher_log_pdf`` are differentiable w.r.t. the
   network output exactly like the reference (only the singular values enter
   autograd there, fisher_utils.py:29-31): the backward multiplies the per-sample
@@ -71,11 +71,32 @@ def KL_Fisher(A, R, overreg=1.05):
     return loss_v
 
 
+class _ProperRotation(torch.autograd.Function):
+    """R = U V^T of the proper SVD and its gradient (closed form of what autograd gives through torch.svd)."""
+
+    @staticmethod
+    def forward(ctx, A):
+        out = _ops.proper_svd(A, rot=True, S=True, U=True, V=True, what="batch_torch_A_to_R")
+        ctx.save_for_backward(out["U"], out["V"], out["S"])
+        ctx.a_shape = A.shape
+        return out["rot"]
+
+    @staticmethod
+    def backward(ctx, g_rot):
+        U, V, S = ctx.saved_tensors
+        return _ops.proper_svd_backward(U, V, S, g_rot).view(ctx.a_shape)
+
+
 def batch_torch_A_to_R(A):
     """Proper-SVD projection onto SO(3), (b,9)|(b,3,3) -> (b,3,3)
-    -- reference fisher_utils.py:39-48."""
+    -- reference fisher_utils.py:39-48.  Differentiable like the reference (the agent never back-propagates
+    it; the plain K1 launch is used unless ``A`` requires a gradient)."""
+    if not _compiling() and _wants_grad(A):
+        return _ProperRotation.apply(A)
     if _compiling():
         from .. import torch_ops  # noqa: F401
+        if _wants_grad(A):
+            return torch.ops.semiuhpe_b200.proper_rotation_full(A)[0]
         return torch.ops.semiuhpe_b200.proper_rotation(A)
     return _ops.proper_svd(A, rot=True, what="batch_torch_A_to_R")["rot"]
 

@@ -7,7 +7,7 @@ formula each -- so that a traced or compiled training step sees them as single n
 
     torch.ops.semiuhpe_b200.fisher_nll(A, R, overreg, want_rot, want_grad, keep) -> (nll, rot, grad)
     torch.ops.semiuhpe_b200.fisher_entropy(A) -> entropy
-    torch.ops.semiuhpe_b200.proper_rotation(A) -> R
+    torch.ops.semiuhpe_b200.proper_rotation(A) -> R          (.._full(A) -> (R, U, V, S), differentiable; polar_backward)
     torch.ops.semiuhpe_b200.fisher_ce(A1, A2, want_grad, target_G, keep) -> (ce, grad)
     torch.ops.semiuhpe_b200.laplace_nll(pred, gt, grids, want_grad, keep) -> (nll, mode, grad)
     torch.ops.semiuhpe_b200.geodesic_deg(pred, gt) -> degrees
@@ -100,6 +100,41 @@ def _(A):
     return _empty_rows(A, _rows(A), 3, 3)
 
 
+@torch.library.custom_op(f"{_NS}::polar_backward", mutates_args=(), device_types="cuda")
+def polar_backward(U: Tensor, V: Tensor, S: Tensor, grad_R: Tensor) -> Tensor:
+    return _ops.proper_svd_backward(U, V, S, grad_R)
+
+
+@polar_backward.register_fake
+def _(U, V, S, grad_R):
+    return _empty_rows(U, _rows(U), 9)
+
+
+@torch.library.custom_op(f"{_NS}::proper_rotation_full", mutates_args=(), device_types="cuda")
+def proper_rotation_full(A: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    out = _ops.proper_svd(A, rot=True, S=True, U=True, V=True, what="batch_torch_A_to_R")
+    return out["rot"], out["U"], out["V"], out["S"]
+
+
+@proper_rotation_full.register_fake
+def _(A):
+    n = _rows(A)
+    return _empty_rows(A, n, 3, 3), _empty_rows(A, n, 3, 3), _empty_rows(A, n, 3, 3), _empty_rows(A, n, 3)
+
+
+def _rotation_setup(ctx, inputs, output):
+    ctx.a_shape = inputs[0].shape
+    ctx.save_for_backward(output[1], output[2], output[3])
+
+
+def _rotation_backward(ctx, g_rot, _gU, _gV, _gS):
+    U, V, S = ctx.saved_tensors
+    return torch.ops.semiuhpe_b200.polar_backward(U, V, S, g_rot.contiguous()).view(ctx.a_shape)
+
+
+proper_rotation_full.register_autograd(_rotation_backward, setup_context=_rotation_setup)
+
+
 @torch.library.custom_op(f"{_NS}::fisher_ce", mutates_args=(), device_types="cuda")
 def fisher_ce(A1: Tensor, A2: Tensor, want_grad: bool, target_G: Optional[Tensor] = None,
               keep: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
@@ -172,4 +207,5 @@ def _(pred, gt):
     return _empty_rows(pred, _rows(pred))
 
 
-OPS = ("scale_rows", "fisher_nll", "fisher_entropy", "proper_rotation", "fisher_ce", "laplace_nll", "geodesic_deg")
+OPS = ("scale_rows", "fisher_nll", "fisher_entropy", "proper_rotation", "proper_rotation_full", "polar_backward",
+       "fisher_ce", "laplace_nll", "geodesic_deg")

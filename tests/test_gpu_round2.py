@@ -426,3 +426,25 @@ def test_err_deg_from_quats_and_formula_known_answers(cuda):
             compute_err_deg_from_matrices(torch.tensor(M, dtype=torch.float32)[None].to(cuda), torch.eye(3)[None].to(cuda))
     for M in kat["trace_in_range_edge"]:
         compute_err_deg_from_matrices(torch.tensor(M, dtype=torch.float32)[None].to(cuda), torch.eye(3)[None].to(cuda))
+
+
+def test_batch_torch_A_to_R_is_differentiable_like_the_reference(cuda):
+    """src/fisher/fisher_utils.py:39-48 back-propagates through torch.svd; ours: the closed-form polar gradient."""
+    from oracle import so3_oracle as orc
+    from semiuhpe_b200.fisher.fisher_utils import batch_torch_A_to_R
+    gen = torch.Generator().manual_seed(17)
+    A = torch.randn(400, 3, 3, generator=gen) * torch.tensor([0.3, 3.0, 10.0, 30.0]).repeat_interleave(100)[:, None, None]
+    W = torch.randn(400, 3, 3, generator=gen)
+    ref = A.double().clone().requires_grad_(True)
+    (orc.a_to_r(ref) * W.double()).sum().backward()
+    leaf = A.to(cuda).requires_grad_(True)
+    R = batch_torch_A_to_R(leaf)
+    assert R.requires_grad
+    (R * W.to(cuda)).sum().backward()
+    g, r = leaf.grad.cpu().double(), ref.grad
+    scale = r.abs().amax(dim=(1, 2)).clamp(min=1e-12)
+    rel = (g - r).abs().amax(dim=(1, 2)) / scale
+    # 1/(s_i + s_j) amplifies fp32 rounding when s2 + s3 is small against s1 (det < 0 matrices): compare per class
+    assert rel.median() < 1e-5 and rel.quantile(0.95) < 2e-4, (rel.median(), rel.quantile(0.95), rel.max())
+    with torch.no_grad():
+        assert not batch_torch_A_to_R(leaf).requires_grad
