@@ -389,14 +389,16 @@ def run_ours(args):
 def k2_traffic(n):
     """DRAM bytes of one K2 launch from the committed ncu capture (never measured in the timed run);
     None when the capture was taken at another launch size."""
-    path = os.path.join(ROOT, "profiles", "r01_k2_traffic.json")
-    if not os.path.exists(path):
-        return None
-    t = json.load(open(path))
-    if t.get("rotations_per_launch") != n:
-        return None
-    return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes": t["algorithmic_bytes"],
-            "source": "profiles/r01_k2_traffic.json (ncu --set full, one launch)"}
+    for name in ("r02_k2_traffic.json", "r01_k2_traffic.json"):          # newest capture first
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        t = json.load(open(path))
+        if t.get("rotations_per_launch") != n:
+            continue
+        return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes": t["algorithmic_bytes"],
+                "source": f"profiles/{name} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}
+    return None
 
 
 def fp32_probe(torch, lib, dev, _capi):

@@ -44,7 +44,10 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 dup(float x) { return pk(x, x); }
 
-constexpr int kStreamThreads = 512;
+#ifndef SUHPE_K2L_THREADS
+#define SUHPE_K2L_THREADS 512
+#endif
+constexpr int kStreamThreads = SUHPE_K2L_THREADS;
 
 // block sums of the packed loop: lo half = even grid points, hi half = odd
 struct PackedSums { f2 z, c, m[9]; };
