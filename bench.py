@@ -409,7 +409,10 @@ def fp32_probe(torch, lib, dev, _capi):
     out = {}
     for variant, name, per in ((0, "ffma", 1), (1, "ffma2", 2), (2, "ffma_mufu", 1), (3, "ffma2_ffma_mixed", 3),
                                (4, "ffma2_plus_lop3", 2), (5, "ffma2_plus_iadd", 2),
-                               (6, "ffma2_imm_addend", 2), (7, "ffma2_bcast_scalar", 2)):
+                               (6, "ffma2_imm_addend", 2), (7, "ffma2_bcast_scalar", 2),
+                               (8, "ffma2_three_distinct_regs", 2), (9, "ffma2_two_distinct_regs_imm", 2),
+                               (10, "ffma2_plus_fsel", 2), (11, "ffma2_plus_fmnmx", 2),
+                               (12, "ffma2_plus_lds128_per8", 2), (13, "ffma2_plus_mufu_per8", 2)):
         for _ in range(2):
             _capi.check(lib.suhpe_fp32_probe(_capi.ptr(sink), variant, iters, blocks, _capi.stream()), "probe")
         torch.cuda.synchronize()

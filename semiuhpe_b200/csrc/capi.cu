@@ -27,7 +27,80 @@ inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 template <int VARIANT>
 __global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters) {
     const float seed = 1.0f + 1e-7f * (float)(threadIdx.x + blockIdx.x);
-    if (VARIANT == 6 || VARIANT == 7) {
+    if (VARIANT >= 10 && VARIANT <= 13) {
+        // issue-mix probes: 8 packed chains; what does one instruction of another pipe cost next to the FFMA2 stream?
+        // 10: every FFMA2 followed by a select (FSEL, ALU pipe)         11: every FFMA2 followed by FMNMX (ALU pipe)
+        // 12: one LDS.128 per 8 FFMA2 (K2's table loads: 4 per 46)      13: one MUFU.EX2 per 8 FFMA2 (K2: 4 per 46)
+        __shared__ float4 tab[256];
+        tab[threadIdx.x] = make_float4(seed, seed + 1.f, seed + 2.f, seed + 3.f);
+        __syncthreads();
+        unsigned long long x[8], a, b;
+        float z[8];
+        const float af = 0.9999f, bf = 1e-4f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(af));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const float v = seed + (float)c; asm("mov.b64 %0, {%1, %1};" : "=l"(x[c]) : "f"(v)); z[c] = v; }
+        const float thr = 1.0f + 1e-7f * (float)blockIdx.x;
+        unsigned sink_bits = threadIdx.x * 2654435761u;
+        unsigned sa = (unsigned)__cvta_generic_to_shared(tab) + 16u * (threadIdx.x & 31);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[c]) : "l"(a), "l"(b));
+                    if (VARIANT == 10) asm volatile("{ .reg .pred p; setp.gt.f32 p, %1, %2; selp.f32 %0, %0, %1, p; }" : "+f"(z[c]) : "f"(thr), "f"(z[(c + 1) & 7]));
+                    if (VARIANT == 11) asm volatile("min.f32 %0, %0, %1;" : "+f"(z[c]) : "f"(thr));
+                }
+                if (VARIANT == 12) {
+                    unsigned v0, v1, v2, v3;                  // consumed on the ALU pipe (LOP3), not by an FMA
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(sa + 512u * (unsigned)((r + i) & 7)));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(sink_bits) : "r"(v0 ^ v2), "r"(v1 ^ v3));
+                }
+                if (VARIANT == 13) {
+                    float y;
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__uint_as_float((sink_bits & 0x007fffffu) | 0x3f800000u)));
+                    asm volatile("xor.b32 %0, %0, %1;" : "+r"(sink_bits) : "r"(__float_as_uint(y)));
+                }
+            }
+        }
+        z[0] += __uint_as_float(sink_bits & 0x3fffffffu);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[c])); acc += lo + hi + z[c]; }
+        if (acc == 123.456f) sink[0] = acc;
+    } else if (VARIANT == 8 || VARIANT == 9) {
+        // operand-bandwidth probes: every packed FMA reads DISTINCT 64-bit registers, none shared between consecutive
+        // instructions (no operand-reuse-cache hits).  8: x[c] = y[c] * z[c] + x[c] (three register pairs, the form of
+        // K2L's sums);  9: x[c] = x[c] * y[c] + immediate (two register pairs, K2's Horner step)
+        unsigned long long x[8], y[8], z[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float v = seed + (float)c;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(x[c]) : "f"(v));
+            // run-time values, different in the two halves: neither an immediate nor a broadcast scalar operand
+            const float t = 1e-7f * (float)(threadIdx.x + 1);
+            const float y0 = 0.9999f + t + 1e-6f * (float)c, y1 = 0.9998f - t + 1e-6f * (float)c;
+            const float z0 = 1.0001f - t - 1e-6f * (float)c, z1 = 1.0002f + t - 1e-6f * (float)c;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(y[c]) : "f"(y0), "f"(y1));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(z[c]) : "f"(z0), "f"(z1));
+        }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (VARIANT == 8) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(x[c]) : "l"(y[c]), "l"(z[c]));
+                    else asm volatile("{ .reg .b64 k; mov.b64 k, {0f38D1B717, 0f38D1B717}; fma.rn.f32x2 %0, %0, %1, k; }" : "+l"(x[c]) : "l"(y[c]));
+                }
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[c])); acc += lo + hi; }
+        if (acc == 123.456f) sink[0] = acc;
+    } else if (VARIANT == 6 || VARIANT == 7) {
         // packed FMA whose addend is an immediate (6) or whose multiplier is a broadcast scalar register (7):
         // the operand forms the Horner bodies of K2 use
         unsigned long long x[8], a;
@@ -158,7 +231,13 @@ cudaError_t launch_fp32_probe(float* sink, int variant, int iters, int blocks, c
     else if (variant == 4) fp32_probe_kernel<4><<<blocks, 256, 0, stream>>>(sink, iters);
     else if (variant == 5) fp32_probe_kernel<5><<<blocks, 256, 0, stream>>>(sink, iters);
     else if (variant == 6) fp32_probe_kernel<6><<<blocks, 256, 0, stream>>>(sink, iters);
-    else fp32_probe_kernel<7><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 7) fp32_probe_kernel<7><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 8) fp32_probe_kernel<8><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 9) fp32_probe_kernel<9><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 10) fp32_probe_kernel<10><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 11) fp32_probe_kernel<11><<<blocks, 256, 0, stream>>>(sink, iters);
+    else if (variant == 12) fp32_probe_kernel<12><<<blocks, 256, 0, stream>>>(sink, iters);
+    else fp32_probe_kernel<13><<<blocks, 256, 0, stream>>>(sink, iters);
     return cudaGetLastError();
 }
 }  // namespace suhpe
@@ -379,7 +458,7 @@ int suhpe_so3_metrics_f32(const float* Rp, const float* Rg, const float* gt_eule
 int suhpe_fp32_probe(float* sink, int32_t variant, int32_t iters, int32_t blocks, void* stream) {
     if (!sink || iters < 1 || blocks < 1 || variant < 0) return SUHPE_EINVAL;
     if (variant >= 100) return rc(launch_body_probe(sink, variant - 100, iters, blocks, st(stream)));
-    if (variant > 7) return SUHPE_EINVAL;
+    if (variant > 13) return SUHPE_EINVAL;
     return rc(launch_fp32_probe(sink, variant, iters, blocks, st(stream)));
 }
 

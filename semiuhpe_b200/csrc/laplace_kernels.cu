@@ -160,6 +160,7 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
     };
     if (single_chunk) { load_chunk(0, p.N); __syncthreads(); }
 
+
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long sample = tile * kStreamThreads + threadIdx.x;
         const bool valid = sample < p.n;

@@ -448,3 +448,39 @@ def test_batch_torch_A_to_R_is_differentiable_like_the_reference(cuda):
     assert rel.median() < 1e-5 and rel.quantile(0.95) < 2e-4, (rel.median(), rel.quantile(0.95), rel.max())
     with torch.no_grad():
         assert not batch_torch_A_to_R(leaf).requires_grad
+
+
+def test_ema_update_keeps_reference_semantics_for_non_fp32_and_strided_entries(cuda):
+    """the EMAN blend must blend EVERY state_dict entry except num_batches_tracked (src/agent.py:290-293) --
+    bf16 / fp64 / channels_last tensors take the reference's own torch expression on the GPU instead of being copied."""
+    from oracle import so3_oracle as orc
+    from semiuhpe_b200.agent import update_ema_variables
+    import copy
+
+    def make():
+        torch.manual_seed(3)
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Conv2d(8, 4, 3))
+        net[2].weight.data = net[2].weight.data.to(memory_format=torch.channels_last)       # strided parameter
+        net.register_buffer("half_buf", torch.randn(7).to(torch.bfloat16))
+        net.register_buffer("dbl_buf", torch.randn(5, dtype=torch.float64))
+        return net
+
+    for eman in (True, False):
+        student, teacher = make().to(cuda), make().to(cuda)
+        with torch.no_grad():
+            for p in student.parameters():
+                p.add_(0.5)
+            student.half_buf.add_(1.0); student.dbl_buf.add_(1.0)
+            student[1].num_batches_tracked.fill_(11)
+        ref_student, ref_teacher = copy.deepcopy(student).cpu(), copy.deepcopy(teacher).cpu()
+        a1 = update_ema_variables(student, teacher, True, 0.999, 100, eman=eman)
+        a2 = orc.update_ema_variables(ref_student, ref_teacher, True, 0.999, 100, eman=eman)
+        assert a1 == a2
+        for (k, v), (_, r) in zip(teacher.state_dict().items(), ref_teacher.state_dict().items()):
+            if v.dtype.is_floating_point:
+                assert torch.allclose(v.cpu().double(), r.double(), rtol=1e-6 if v.dtype != torch.bfloat16 else 1e-2, atol=1e-7), k
+            else:
+                assert torch.equal(v.cpu(), r), k
+        if eman:
+            assert int(teacher[1].num_batches_tracked) == 11
+            assert not torch.equal(teacher.half_buf, student.half_buf)            # blended, not copied
