@@ -343,6 +343,7 @@ def run_ours(args):
     roofline = {
         "bound": "fp32", "kernel": "fisher_fused_kernel", "achieved": achieved_tflops, "peak": peak_tflops,
         "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
+        "frac_all_nodes_evaluated": n * FLOP_PER_ROTATION / (fused_all_ms * 1e-3) / 1e12 / peak_tflops,
         "peak_source": "FP32 FMA micro-benchmark run on this GPU in this process (suhpe_fp32_probe; MEASURED_PEAKS.json "
                        "has no FP32-pipe figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
         "algorithmic_flop_per_rotation": FLOP_PER_ROTATION, "rotations_per_launch": n, "kernel_ms": fused_ms,
