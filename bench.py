@@ -214,7 +214,6 @@ def run_ours(args):
     from semiuhpe_b200 import _capi, _ops
     import semiuhpe_b200
     from semiuhpe_b200.agent import pool_index, _quat_to_matrix
-    from semiuhpe_b200.distributed import CudaHistogramBackend
     semiuhpe_b200.set_error_checking(False)          # sync-free steps; finiteness is asserted after the run
     lib = _capi.lib()
 

@@ -136,7 +136,8 @@ class on_device:
 
 
 def as_records(t, name, width=9):
-    """Contiguous fp32 CUDA (n,width) view of a (n,width) / (n,3,3) tensor.
+    """Contiguous fp32 CUDA tensor whose memory is n records of ``width`` floats and whose ``shape[0]`` is n
+    (the input itself when it already is (n,width) / (n,3,3) and contiguous, else a detached reshaped copy).
 
     The reference reshapes with ``view``/``reshape`` (fisher_utils.py:15,41,75) and
     works in fp32; non-CUDA input is an error here (no CPU path)."""
@@ -154,5 +155,7 @@ def as_records(t, name, width=9):
         # tensor silently reinterpreted as n/3 matrices is far more likely a bug than an intent
         raise RuntimeError(f"{name}: expected trailing dimensions ({width},)" + (" or (3, 3)" if width == 9 else "")
                            + f", got shape {tuple(shape)}")
+    if t.is_contiguous() and 2 <= len(shape) <= (3 if width == 9 else 2):
+        return t                              # (n,width) / (n,3,3) as it is: callers only take its pointer and shape[0]
     t = t.detach().reshape(-1, width)
     return t if t.is_contiguous() else t.contiguous()

@@ -448,7 +448,8 @@ class SslStep:
                 ptr(status), stream(idx)), "ssl_step")
         _raise_from_status(status, "ssl_step")
         out = dict(losses=losses, grad_l=None if grad_l is None else grad_l.view(b_l, 9),
-                   grad_strong=None if grad_s is None else grad_s.view(b_u, 9))
+                   grad_strong=None if grad_s is None else grad_s.view(b_u, 9),
+                   grads=flat[4:4 + (b_l + b_u) * 9].view(b_l + b_u, 9) if want_grad else None)
         if extras:
             out.update(pred_orth=rest.view(b_l, 3, 3), entropy=ent, mask=mask, pseudo=None if pseudo is None else pseudo.view(b_u, 3, 3),
                        losses_l=nll_l, losses_u=loss_u)

@@ -211,17 +211,20 @@ class _SslLoss(torch.autograd.Function):
             out_l, gt, pred_weak, pred_strong, opts["conf_thres"], aug_rot=aug_rot, aug_mode=opts["aug_mode"],
             overreg=opts["overreg"], ssl_lambda=opts["ssl_lambda"], unsup=opts["unsup"], want_grad=want_grad)
         if want_grad:
-            ctx.save_for_backward(res["grad_l"], res["grad_strong"])
+            ctx.save_for_backward(res["grads"])          # both gradients, contiguous: (b_l + b_u, 9)
+        ctx.rows = (b_l, b_u)
         ctx.shapes = (out_l.shape, None if pred_strong is None else pred_strong.shape)
         opts["result"] = res
         return res["losses"][3]
 
     @staticmethod
     def backward(ctx, g):
-        grad_l, grad_s = ctx.saved_tensors
+        (grads,) = ctx.saved_tensors
+        b_l, b_u = ctx.rows
         shape_l, shape_s = ctx.shapes
-        gl = _ops.scale_rows(grad_l, scalar_weight=g).view(shape_l)
-        gs = None if shape_s is None or grad_s is None else _ops.scale_rows(grad_s, scalar_weight=g).view(shape_s)
+        scaled = _ops.scale_rows(grads, scalar_weight=g)                  # one launch for both student outputs
+        gl = scaled[:b_l].view(shape_l)
+        gs = None if shape_s is None or b_u == 0 else scaled[b_l:].view(shape_s)
         return gl, gs, None, None, None, None
 
 

@@ -2,7 +2,6 @@
 import the reference's agent afterwards -- against a minimal fake ``src`` tree, and against the real reference
 tree when it is present (this container; the GPU box has no /root/reference).  No kernel runs: the checks
 are about which function objects the reference ends up bound to."""
-import importlib
 import os
 import subprocess
 import sys
