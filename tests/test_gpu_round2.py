@@ -484,3 +484,57 @@ def test_ema_update_keeps_reference_semantics_for_non_fp32_and_strided_entries(c
         if eman:
             assert int(teacher[1].num_batches_tracked) == 11
             assert not torch.equal(teacher.half_buf, student.half_buf)            # blended, not copied
+
+
+def test_two_streams_do_not_interact(cuda):
+    """Re-entrancy: the same entry points on two streams at once (each with its own status word, select workspace and
+    SSL-step handle) give the results of running them one after the other."""
+    import semiuhpe_b200
+    from semiuhpe_b200.agent import dynamic_entropy_filter, ssl_loss
+    from semiuhpe_b200 import _ops
+    gen = torch.Generator().manual_seed(41)
+    A = [(10 * torch.randn(200000, 9, generator=gen)).to(cuda) for _ in range(2)]
+    A_l, R_l, W, S = (t.to(cuda) for t in _batch(gen))
+    serial = []
+    for a in A:
+        ent, mask, ratio, thr = dynamic_entropy_filter(a, 0.9)
+        serial.append((ent.clone(), mask.clone(), thr))
+    ref_loss = ssl_loss(A_l, R_l, W, S, -4.0)[0].clone()
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    out = [None, None]
+    semiuhpe_b200.set_error_checking(False)
+    try:
+        for rep in range(3):
+            for i, st in enumerate(streams):
+                st.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(st):
+                    ent, mask, ratio = dynamic_entropy_filter(A[i], 0.9, return_threshold=False)
+                    loss = ssl_loss(A_l, R_l, W, S, -4.0)[0]
+                    out[i] = (ent, mask, loss)
+        torch.cuda.synchronize()
+    finally:
+        semiuhpe_b200.set_error_checking(True)
+    for i in range(2):
+        assert torch.equal(out[i][0], serial[i][0]) and torch.equal(out[i][1], serial[i][1])
+        assert torch.equal(out[i][2], ref_loss)
+
+
+def test_extreme_scales_stay_finite_and_proper(cuda):
+    """Parameter matrices from 1e-30 to 1e+30 (the SVD prescales by an exact power of two): rotations stay proper and
+    finite, entropies of tiny matrices tend to 0 like the reference's, nothing hangs or raises."""
+    from semiuhpe_b200.fisher.fisher_utils import batch_torch_A_to_R, fisher_entropy, vmf_loss
+    gen = torch.Generator().manual_seed(43)
+    base = torch.randn(64, 9, generator=gen)
+    for scale in (1e-30, 1e-12, 1e-3, 1.0, 1e3, 1e12, 1e30):
+        A = (base * scale).to(cuda)
+        R = batch_torch_A_to_R(A)
+        assert bool(torch.isfinite(R).all())
+        eye = torch.eye(3, device=cuda).expand(64, 3, 3)
+        assert float((R @ R.transpose(1, 2) - eye).abs().max()) < 1e-5
+        assert float((torch.det(R) - 1).abs().max()) < 1e-5
+        if scale <= 1e-3:
+            ent = fisher_entropy(A)
+            assert bool(torch.isfinite(ent).all()) and float(ent.abs().max()) < 1e-4     # uniform density: H -> 0
+            loss, _ = vmf_loss(A, R, overreg=1.025)
+            assert bool(torch.isfinite(loss).all())
