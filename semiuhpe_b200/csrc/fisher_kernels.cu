@@ -24,9 +24,13 @@
 //   phase 3  thread-per-sample : closing arithmetic, gradient
 //            -R_gt + overreg * U diag(g) V^T, entropy, staged float4 stores; with `hist` the first
 //            radix-select digit of the entropy key is counted right here (warp-aggregated RED.ADD)
-// Geometry: one persistent CTA of 24 warps per SM (79 registers: the per-sample state of phase 3
-// rides through phase 2 in shared memory), 27 KB of node tables shared by the CTA + 8.25 KB of
-// scratch per warp in dynamic shared memory (225 KB).
+// Geometry: one persistent CTA of 24 warps per SM (78 registers: the per-sample state of phase 3
+// rides through phase 2 in shared memory and the 64-bit tile base is re-derived after it), 27 KB of
+// node tables shared by the CTA + 8.25 KB of scratch per warp in dynamic shared memory (225 KB).
+// What the replay is sensitive to (measured): instruction count and code size -- not
+// latency, not the SFU.  Hence 64-pair passes that are not unrolled, Horner chains written round
+// robin so that ptxas keeps them interleaved under the register cap, and one butterfly for the
+// four warp sums of a rotation.
 #include "kernels.cuh"
 #include "so3_math.cuh"
 #include <cstddef>

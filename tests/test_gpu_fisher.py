@@ -185,7 +185,7 @@ def test_full_size_properties(cuda):
 
 
 def test_negligible_node_cut_on_off(cuda, golden):
-    """K2 skips the provably negligible node prefix by default (suhpe_set_quadrature_cut_bits, 26);
+    """K2 skips the provably negligible node prefix by default (cut_bits = 26, a per-call argument of the C ABI);
     evaluating all 512 nodes (bits=0) must give the same numbers to fp32 rounding, and both
     settings must hold the golden parity."""
     import semiuhpe_b200
