@@ -221,14 +221,19 @@ int suhpe_pipeline_sync(suhpe_pipeline* p);
  * Optional outputs (nullable): Rest_l (b_l,9), entropy (b_u), mask (b_u), pseudo (b_u,9) = the projected
  * pseudo labels of every row, losses_l (b_l), losses_u (b_u, zero for filtered rows).
  * b_u may be 0 (supervised step, train_func_s1: src/agent.py:253-270); then only the labeled part runs.
- * The handle owns the forked streams, their events and the device scratch; one call at a time per handle. */
+ * workspace: suhpe_ssl_step_workspace_floats(b_l, b_u) floats of caller-owned device scratch, 16-byte aligned, private to
+ * the call until the work queued on `stream` has run.  The handle owns only the two forked streams and their events --
+ * no data -- so one handle per device serves every caller stream (calls from different streams serialise their forked
+ * branches but do not share a byte), and nothing is allocated inside the call: it can be issued during stream capture. */
 typedef struct suhpe_ssl_step suhpe_ssl_step;
-int suhpe_ssl_step_create(suhpe_ssl_step** out, int64_t max_labeled, int64_t max_unlabeled);
+int suhpe_ssl_step_create(suhpe_ssl_step** out);
 int suhpe_ssl_step_destroy(suhpe_ssl_step* ctx);
+int64_t suhpe_ssl_step_workspace_floats(int64_t b_l, int64_t b_u);
 int suhpe_ssl_step_f32(suhpe_ssl_step* ctx, const float* out_l, const float* gt_l, int64_t b_l,
                        const float* pred_weak, const float* pred_strong, int64_t b_u,
                        const float* aug_rot, int32_t aug_mode, const float* conf_thres_dev, float conf_thres_host,
                        float overreg, float ssl_lambda, int32_t unsup_kind, int32_t cut_bits,
+                       float* workspace,
                        float* losses, float* grad_l, float* grad_strong,
                        float* Rest_l, float* entropy, uint8_t* mask, float* pseudo, float* losses_l, float* losses_u,
                        int* status, void* stream);

@@ -45,10 +45,11 @@ SIGNATURES = {
                                                 ctypes.POINTER(f32), ctypes.POINTER(u64)]),
     "suhpe_fisher_pool_host": (ctypes.c_int, [c_vp, c_vp, c_vp, i64, f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "suhpe_pipeline_sync": (ctypes.c_int, [c_vp]),
-    "suhpe_ssl_step_create": (ctypes.c_int, [ctypes.POINTER(c_vp), i64, i64]),
+    "suhpe_ssl_step_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
     "suhpe_ssl_step_destroy": (ctypes.c_int, [c_vp]),
+    "suhpe_ssl_step_workspace_floats": (i64, [i64, i64]),
     "suhpe_ssl_step_f32": (ctypes.c_int, [c_vp, c_vp, c_vp, i64, c_vp, c_vp, i64, c_vp, i32, c_vp, f32, f32, f32, i32, i32,
-                                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 # include/semiuhpe_b200_probe.h (measurement entry points, not part of the drop-in boundary)
 PROBE_SIGNATURES = {

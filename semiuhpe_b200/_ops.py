@@ -373,16 +373,17 @@ def entropy_mask(entropy, thr, ws=None, want_mask=True):
 class SslStep:
     """Handle of ``suhpe_ssl_step_f32``: the loss head of a whole semi-supervised step -- supervised Fisher NLL,
     teacher entropy, mask, rotate-augmentation adjustment, fisher_CE (or NLL) against the pseudo labels, the
-    means, ``loss_all`` and its gradients -- as one C call (a fixed launch sequence over three forked streams)."""
+    means, ``loss_all`` and its gradients -- as one C call (a fixed launch sequence over three forked streams).
+    The handle holds two side streams and three events, no data: the scratch of a call is a torch allocation, so
+    nothing is allocated by the library inside the call and the step can be issued during CUDA-graph capture."""
 
-    def __init__(self, max_labeled, max_unlabeled, device=None):
+    def __init__(self, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("SslStep needs a CUDA device: semiuhpe_b200 has no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.max_l, self.max_u = int(max_labeled), int(max_unlabeled)
         self._h = ctypes.c_void_p()
         with on_device(self.device):
-            check(lib().suhpe_ssl_step_create(ctypes.byref(self._h), self.max_l, self.max_u), "ssl_step_create")
+            check(lib().suhpe_ssl_step_create(ctypes.byref(self._h)), "ssl_step_create")
 
     def close(self):
         if self._h:
@@ -413,8 +414,8 @@ class SslStep:
                 R9 = as_records(aug_rot, "aug_rot_mat")
                 if R9.shape[0] != b_u:
                     raise RuntimeError(f"shape mismatch: {b_u} teacher outputs, {R9.shape[0]} augmentation rotations")
-        if b_l == 0 or b_l > self.max_l or b_u > self.max_u:
-            raise ValueError(f"ssl step of {b_l}+{b_u} rows exceeds the handle's capacity {self.max_l}+{self.max_u} (or is empty)")
+        if b_l == 0:
+            raise ValueError("ssl step without labeled rows")
         if unsup not in ("ce", "nll"):
             raise ValueError(f"unknown unsupervised loss {unsup!r}")
         dev = L9.device
@@ -422,7 +423,10 @@ class SslStep:
         sizes = [4, b_l * 9 if want_grad else 0, b_u * 9 if want_grad else 0]
         if extras:
             sizes += [b_l * 9, b_u, b_u * 9, b_l, b_u]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        n_work = int(lib().suhpe_ssl_step_workspace_floats(b_l, b_u))
+        tail = (-sum(sizes)) % 4                                   # the workspace starts on a 16-byte boundary
+        flat = torch.empty(sum(sizes) + tail + n_work, dtype=torch.float32, device=dev)
+        work = flat[sum(sizes) + tail:]
         parts, off = [], 0
         for sz in sizes:
             parts.append(flat[off:off + sz] if sz else None)
@@ -443,7 +447,7 @@ class SslStep:
             status = _status_word(dev)
             check(lib().suhpe_ssl_step_f32(
                 self._h, ptr(L9), ptr(G9), b_l, ptr(W9), ptr(S9), b_u, ptr(R9), int(aug_mode), thr_dev, thr_host,
-                float(overreg), float(ssl_lambda), 0 if unsup == "ce" else 1, _cut(cut_bits),
+                float(overreg), float(ssl_lambda), 0 if unsup == "ce" else 1, _cut(cut_bits), ptr(work),
                 ptr(losses), ptr(grad_l), ptr(grad_s), ptr(rest), ptr(ent), ptr(mask), ptr(pseudo), ptr(nll_l), ptr(loss_u),
                 ptr(status), stream(idx)), "ssl_step")
         _raise_from_status(status, "ssl_step")

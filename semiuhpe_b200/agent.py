@@ -188,14 +188,14 @@ def validation_terms(pred, pred_orth, gt, conf_thres, gt_euler=None):
 _SSL_STEPS = {}
 
 
-def _ssl_handle(device, b_l, b_u):
+def _ssl_handle(device):
+    """One handle (two side streams + three events, no data) per device and host thread."""
+    import threading
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    key = (idx, _ops.stream(idx))
+    key = (idx, threading.get_ident())
     h = _SSL_STEPS.get(key)
-    if h is None or h.max_l < b_l or h.max_u < b_u:
-        if h is not None:
-            h.close()
-        h = _SSL_STEPS[key] = _ops.SslStep(max(b_l, 64), max(b_u, 256), torch.device("cuda", idx))
+    if h is None:
+        h = _SSL_STEPS[key] = _ops.SslStep(torch.device("cuda", idx))
     return h
 
 
@@ -207,7 +207,7 @@ class _SslLoss(torch.autograd.Function):
         want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         b_l = out_l.reshape(-1, 9).shape[0]
         b_u = 0 if pred_weak is None else pred_weak.reshape(-1, 9).shape[0]
-        res = _ssl_handle(out_l.device, b_l, b_u).run(
+        res = _ssl_handle(out_l.device).run(
             out_l, gt, pred_weak, pred_strong, opts["conf_thres"], aug_rot=aug_rot, aug_mode=opts["aug_mode"],
             overreg=opts["overreg"], ssl_lambda=opts["ssl_lambda"], unsup=opts["unsup"], want_grad=want_grad)
         if want_grad:
@@ -240,7 +240,9 @@ def ssl_loss(fisher_out, gt, pred_weak=None, pred_strong=None, conf_thres=0.0, *
     Returns ``(loss_all, info)``: ``loss_all`` is a scalar tensor with autograd history to ``fisher_out`` and
     ``pred_strong``; ``info`` holds detached device tensors -- ``loss``, ``unsuper_loss`` (already x mask ratio),
     ``mask_ratio``, ``pred_orth`` (b,3,3), ``entropy``, ``mask``, ``pseudo_labels`` (every row), ``losses``,
-    ``unsuper_losses`` (0 on filtered rows).  No host synchronisation with error checking off."""
+    ``unsuper_losses`` (0 on filtered rows).  No host synchronisation with error checking off, and no allocation
+    by the library inside the call (the scratch is a torch allocation): the step works under
+    ``torch.cuda.graph`` / ``torch.cuda.make_graphed_callables`` once the first eager call on the device has run."""
     if type_unsuper not in ("ce", "nll"):
         raise ValueError(f"ssl_loss: unknown type_unsuper {type_unsuper!r}")
     if train_labeled not in ("DAD3DHeads", "300WLP"):

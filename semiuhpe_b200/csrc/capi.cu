@@ -263,18 +263,10 @@ struct suhpe_pipeline {
 };
 
 // ---- SSL loss head -------------------------------------------------------------
+// the handle owns only the two forked streams and their events; every byte of scratch comes from the caller
 struct suhpe_ssl_step {
-    long long max_l, max_u;
     cudaStream_t s_a, s_b;                  // forked branches (the caller's stream carries the teacher branch)
     cudaEvent_t ev_fork, ev_a, ev_b;
-    float* nll_l;                           // (max_l)
-    float* ent;                             // (max_u)
-    float* work;                            // (10 * max_u): G1 | S2 | G2 | H2, the fisher_CE workspace layout
-    float* adjusted;                        // (max_u,9)
-    float* pseudo;                          // (max_u,9)
-    float* loss_u;                          // (max_u)
-    uint8_t* mask;                          // (max_u)
-    unsigned long long* kept;
 };
 
 extern "C" {
@@ -625,51 +617,63 @@ int suhpe_ssl_step_destroy(suhpe_ssl_step* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
-    cudaFree(c->nll_l); cudaFree(c->ent); cudaFree(c->work); cudaFree(c->adjusted); cudaFree(c->pseudo);
-    cudaFree(c->loss_u); cudaFree(c->mask); cudaFree(c->kept);
     delete c;
     return 0;
 }
 
-int suhpe_ssl_step_create(suhpe_ssl_step** out, int64_t max_labeled, int64_t max_unlabeled) {
-    if (!out || max_labeled <= 0 || max_unlabeled < 0) return SUHPE_EINVAL;
+int suhpe_ssl_step_create(suhpe_ssl_step** out) {
+    if (!out) return SUHPE_EINVAL;
     suhpe_ssl_step* c = new (std::nothrow) suhpe_ssl_step();
     if (!c) return SUHPE_EINVAL;
     memset(c, 0, sizeof(*c));
-    c->max_l = max_labeled; c->max_u = max_unlabeled;
-    const size_t mu = (size_t)(max_unlabeled > 0 ? max_unlabeled : 1);
-    cudaError_t e = cudaSuccess;
-    auto A = [&](void** q, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(q, bytes); };
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_a, cudaStreamNonBlocking);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->s_a, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_b, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming);
-    A((void**)&c->nll_l, (size_t)max_labeled * 4);
-    A((void**)&c->ent, mu * 4); A((void**)&c->work, mu * 4 * SUHPE_FISHER_CE_WORKSPACE_FLOATS);
-    A((void**)&c->adjusted, mu * 36); A((void**)&c->pseudo, mu * 36); A((void**)&c->loss_u, mu * 4);
-    A((void**)&c->mask, mu); A((void**)&c->kept, sizeof(unsigned long long));
     if (e != cudaSuccess) { suhpe_ssl_step_destroy(c); return rc(e); }
     *out = c;
     return 0;
+}
+
+int64_t suhpe_ssl_step_workspace_floats(int64_t b_l, int64_t b_u) {
+    if (b_l < 0 || b_u < 0) return 0;
+    // kept counter | nll_l | entropy | fisher_CE workspace (G1 S2 G2 H2) | adjusted | pseudo | loss_u | mask bytes,
+    // every region rounded up to a multiple of 4 floats (the carving in suhpe_ssl_step_f32)
+    auto up4 = [](int64_t v) { return (v + 3) & ~(int64_t)3; };
+    return 4 + up4(b_l) + up4(b_u) + up4(SUHPE_FISHER_CE_WORKSPACE_FLOATS * b_u) + up4(9 * b_u) + up4(9 * b_u) + up4(b_u) +
+           up4((b_u + 3) / 4);
 }
 
 int suhpe_ssl_step_f32(suhpe_ssl_step* c, const float* out_l, const float* gt_l, int64_t b_l,
                        const float* pred_weak, const float* pred_strong, int64_t b_u,
                        const float* aug_rot, int32_t aug_mode, const float* conf_thres_dev, float conf_thres_host,
                        float overreg, float ssl_lambda, int32_t unsup_kind, int32_t cut_bits,
+                       float* workspace,
                        float* losses, float* grad_l, float* grad_strong,
                        float* Rest_l, float* entropy, uint8_t* mask, float* pseudo, float* losses_l, float* losses_u,
                        int* status, void* stream) {
-    if (!c || !losses || b_l <= 0 || b_l > c->max_l || b_u < 0 || b_u > c->max_u || !out_l || !gt_l) return SUHPE_EINVAL;
+    if (!c || !losses || !workspace || b_l <= 0 || b_u < 0 || !out_l || !gt_l) return SUHPE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) return SUHPE_EINVAL;
     if (b_u > 0 && (!pred_weak || !pred_strong)) return SUHPE_EINVAL;
     if (unsup_kind < 0 || unsup_kind > 1 || (aug_rot && (aug_mode < 0 || aug_mode > 1))) return SUHPE_EINVAL;
     const int bits = clamp_cut_bits(cut_bits);
     cudaStream_t S = st(stream);
-    float* nll_l = losses_l ? losses_l : c->nll_l;
-    float* ent = entropy ? entropy : c->ent;
-    uint8_t* msk = mask ? mask : c->mask;
-    float* pse = pseudo ? pseudo : c->pseudo;
+    // carve the workspace (every region starts on a multiple of 4 floats = 16 bytes)
+    auto up4 = [](int64_t v) { return (v + 3) & ~(int64_t)3; };
+    float* w = workspace;
+    unsigned long long* kept = reinterpret_cast<unsigned long long*>(w);  w += 4;
+    float* ws_nll = w;        w += up4(b_l);
+    float* ws_ent = w;        w += up4(b_u);
+    float* ws_work = w;       w += up4(SUHPE_FISHER_CE_WORKSPACE_FLOATS * b_u);
+    float* ws_adjusted = w;   w += up4(9 * b_u);
+    float* ws_pseudo = w;     w += up4(9 * b_u);
+    float* ws_loss_u = w;     w += up4(b_u);
+    uint8_t* ws_mask = reinterpret_cast<uint8_t*>(w);
+    float* nll_l = losses_l ? losses_l : ws_nll;
+    float* ent = entropy ? entropy : ws_ent;
+    uint8_t* msk = mask ? mask : ws_mask;
+    float* pse = pseudo ? pseudo : ws_pseudo;
     cudaError_t e = cudaSuccess;
 #define CK(x) do { if (e == cudaSuccess) e = (x); } while (0)
     // fork: the supervised quadrature (and, for 'ce', the student's unlabeled quadrature) run beside the teacher branch
@@ -683,12 +687,12 @@ int suhpe_ssl_step_f32(suhpe_ssl_step* c, const float* out_l, const float* gt_l,
         CK(cudaEventRecord(c->ev_a, c->s_a));
     }
     if (b_u > 0) {
-        float* G1 = c->work;
+        float* G1 = ws_work;
         if (unsup_kind == 0) {
             CK(cudaStreamWaitEvent(c->s_b, c->ev_fork, 0));
             FisherArgs q{};                       // student, unlabeled: the statistics fisher_CE needs of the prediction
             q.A = pred_strong; q.n = (long long)b_u; q.overreg = 1.0f;
-            q.S = c->work + 3 * b_u; q.G = c->work + 6 * b_u; q.entropy = c->work + 9 * b_u;
+            q.S = ws_work + 3 * b_u; q.G = ws_work + 6 * b_u; q.entropy = ws_work + 9 * b_u;
             q.status = nullptr;                   // non-finite rows are reported by the closing kernel, for kept rows only
             q.cut_bits = bits;
             CK(launch_fisher_fused(q, c->s_b));
@@ -698,12 +702,12 @@ int suhpe_ssl_step_f32(suhpe_ssl_step* c, const float* out_l, const float* gt_l,
         t.A = pred_weak; t.n = (long long)b_u; t.overreg = 1.0f; t.entropy = ent; t.G = unsup_kind == 0 ? G1 : nullptr;
         t.status = status; t.cut_bits = bits;
         CK(launch_fisher_fused(t, S));
-        CK(cudaMemsetAsync(c->kept, 0, sizeof(unsigned long long), S));
-        CK(launch_mask(ent, (long long)b_u, conf_thres_dev, conf_thres_host, msk, c->kept, S));
+        CK(cudaMemsetAsync(kept, 0, sizeof(unsigned long long), S));
+        CK(launch_mask(ent, (long long)b_u, conf_thres_dev, conf_thres_host, msk, kept, S));
         const float* adjusted = pred_weak;
         if (aug_rot) {
-            CK(launch_rotate_adjust(pred_weak, aug_rot, (long long)b_u, (int)aug_mode, c->adjusted, S));
-            adjusted = c->adjusted;
+            CK(launch_rotate_adjust(pred_weak, aug_rot, (long long)b_u, (int)aug_mode, ws_adjusted, S));
+            adjusted = ws_adjusted;
         }
         if (unsup_kind == 1 || pseudo) {
             SvdArgs sv{adjusted, (long long)b_u, pse, nullptr, nullptr, nullptr, status, false};
@@ -711,12 +715,12 @@ int suhpe_ssl_step_f32(suhpe_ssl_step* c, const float* out_l, const float* gt_l,
         }
         if (unsup_kind == 0) {
             CK(cudaStreamWaitEvent(S, c->ev_b, 0));
-            FisherCeArgs ce{adjusted, pred_strong, (long long)b_u, G1, c->work + 3 * b_u, c->work + 6 * b_u, c->work + 9 * b_u,
-                            c->loss_u, grad_strong, status, msk};
+            FisherCeArgs ce{adjusted, pred_strong, (long long)b_u, G1, ws_work + 3 * b_u, ws_work + 6 * b_u, ws_work + 9 * b_u,
+                            ws_loss_u, grad_strong, status, msk};
             CK(launch_fisher_ce_close(ce, S));
         } else {
             FisherArgs q{};                       // 'nll': the student's Fisher NLL against the projected pseudo labels
-            q.A = pred_strong; q.Rgt = pse; q.n = (long long)b_u; q.overreg = overreg; q.nll = c->loss_u; q.grad = grad_strong;
+            q.A = pred_strong; q.Rgt = pse; q.n = (long long)b_u; q.overreg = overreg; q.nll = ws_loss_u; q.grad = grad_strong;
             q.status = status; q.keep = msk; q.cut_bits = bits;
             CK(launch_fisher_fused(q, S));
         }
@@ -724,8 +728,8 @@ int suhpe_ssl_step_f32(suhpe_ssl_step* c, const float* out_l, const float* gt_l,
     CK(cudaStreamWaitEvent(S, c->ev_a, 0));
     SslFinalizeArgs f{};
     f.nll_l = nll_l; f.b_l = (long long)b_l; f.grad_l = grad_l;
-    f.loss_u = c->loss_u; f.b_u = (long long)b_u; f.grad_u = b_u > 0 ? grad_strong : nullptr;
-    f.mask = msk; f.kept = c->kept; f.ssl_lambda = ssl_lambda; f.losses = losses; f.losses_u_out = b_u > 0 ? losses_u : nullptr;
+    f.loss_u = ws_loss_u; f.b_u = (long long)b_u; f.grad_u = b_u > 0 ? grad_strong : nullptr;
+    f.mask = msk; f.kept = kept; f.ssl_lambda = ssl_lambda; f.losses = losses; f.losses_u_out = b_u > 0 ? losses_u : nullptr;
     CK(launch_ssl_finalize(f, S));
 #undef CK
     return rc(e);

@@ -52,8 +52,11 @@ def test_ctypes_table_matches_header(built):
     assert handle.suhpe_fisher_fused_f32(None, None, 5, 1.0, 26, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_scale_rows_f32(None, 3, 9, None, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_scale_rows_f32(None, 0, 9, None, None, None, None, None) == 0
-    assert handle.suhpe_ssl_step_f32(None, None, None, 1, None, None, 0, None, 0, None, 0.0, 1.0, 1.0, 0, 26,
+    assert handle.suhpe_ssl_step_f32(None, None, None, 1, None, None, 0, None, 0, None, 0.0, 1.0, 1.0, 0, 26, None,
                                      None, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
+    # scratch of the one-call SSL step: every region a multiple of 4 floats, so the carving stays 16-byte aligned
+    assert handle.suhpe_ssl_step_workspace_floats(32, 128) == 4 + 32 + 128 + 1280 + 1152 + 1152 + 128 + 32
+    assert handle.suhpe_ssl_step_workspace_floats(5, 0) == 4 + 8 and handle.suhpe_ssl_step_workspace_floats(1, 1) % 4 == 0
     assert handle.suhpe_entropy_threshold_f32(None, 0, 0, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_laplace_nll_f32(None, None, 1, None, 0, None, None, None, None, None, None) == _capi.EINVAL
     assert handle.suhpe_ema_update_f32(None, None, None, 3, 0.5, 0.5, 0, None) == _capi.EINVAL

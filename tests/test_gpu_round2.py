@@ -538,3 +538,33 @@ def test_extreme_scales_stay_finite_and_proper(cuda):
             assert bool(torch.isfinite(ent).all()) and float(ent.abs().max()) < 1e-4     # uniform density: H -> 0
             loss, _ = vmf_loss(A, R, overreg=1.025)
             assert bool(torch.isfinite(loss).all())
+
+
+def test_make_graphed_callables_on_the_ssl_step(cuda):
+    """The stock PyTorch route to a graph-replayed training step (torch.cuda.make_graphed_callables: warm-up on a
+    side stream, forward and backward captured separately) works on the one-call loss head: the library allocates
+    nothing inside the call and its handle is per device, not per stream."""
+    import semiuhpe_b200
+    from semiuhpe_b200.agent import ssl_loss
+    gen = torch.Generator().manual_seed(51)
+    A_l, R_l, W, S = (t.to(cuda) for t in _batch(gen))
+
+    def head(out_l, strong, gt, weak):
+        return ssl_loss(out_l, gt, weak, strong, -4.0, SSL_lambda=0.3)[0]
+
+    semiuhpe_b200.set_error_checking(False)
+    try:
+        sample = (A_l.clone().requires_grad_(True), S.clone().requires_grad_(True), R_l.clone(), W.clone())
+        graphed = torch.cuda.make_graphed_callables(head, sample)
+        for shift in (0.0, 0.25):
+            l1, s1 = (A_l + shift).requires_grad_(True), (S - shift).requires_grad_(True)
+            out = graphed(l1, s1, R_l, W)
+            out.backward()
+            l2, s2 = (A_l + shift).requires_grad_(True), (S - shift).requires_grad_(True)
+            ref = head(l2, s2, R_l, W)
+            ref.backward()
+            torch.cuda.synchronize()
+            assert torch.equal(out.detach(), ref.detach())
+            assert torch.equal(l1.grad, l2.grad) and torch.equal(s1.grad, s2.grad)
+    finally:
+        semiuhpe_b200.set_error_checking(True)
