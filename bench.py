@@ -472,7 +472,7 @@ def run_e2e(torch, dist, dev, n, args, world, rank, k, cores=None):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    steps = max(2, min(args.steps, 5))
+    steps = max(2, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(steps):
         res = pipe.run(A_h, R_h, OVERREG, LEFT_RATIO, group=group)   # blocking call: results are on the host on return
