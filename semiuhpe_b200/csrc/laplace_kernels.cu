@@ -14,12 +14,16 @@
 // FP32 FMA only: the reference forbids TF32 here (rotation_laplace.py:13), and a
 // K=9 contraction has no tensor-core shape anyway.
 //
-// Two decompositions of the same sum:
-//   stream  thread per sample (large batches): 512-thread persistent CTAs; the grid sits in shared
-//           memory as interleaved point PAIRS so one LDS.128 broadcast feeds two f32x2 operands and
-//           every FMA of the loop is a packed FFMA2 over two grid points (28 per pair); block sums
-//           fold into the totals every 128 points so the fp32 summation error does not grow with N
+// Three decompositions of the same sum:
+//   stream2 thread per TWO samples (>= 1024 samples per SM): 512-thread persistent CTAs; a thread keeps its two
+//           samples in the halves of packed registers and the grid point is the broadcast scalar operand, so every
+//           FMA of the loop is a packed FFMA2 in the two-register-pair form (25 packed ops and 2.25 LDS.128 per
+//           sample and 2 grid points); one comparison per sample and trip covers the clamp and the exponent offset
+//   stream  thread per sample (>= 256 samples per SM): the grid sits in shared memory as interleaved point PAIRS
+//           and the packed halves are two grid points (28 packed ops per pair of points)
 //   warp    warp per sample (small batches): lanes stride the grid, shuffle merge
+// Both stream forms fold their block sums into the totals every 128 points so the fp32 summation error does not
+// grow with N.
 // Per-sample set-up (proper SVD, T, the ground-truth term) runs in fp64: see laplace_setup.
 #include "kernels.cuh"
 #include "so3_math.cuh"
@@ -28,6 +32,9 @@ namespace suhpe {
 
 namespace {
 
+#ifndef SUHPE_K2L_PACK_SAMPLES
+#define SUHPE_K2L_PACK_SAMPLES 1     // 0: never use the sample-packed stream kernel (A/B builds)
+#endif
 #ifndef SUHPE_K2L_NEWTON
 #define SUHPE_K2L_NEWTON 0      // 1 = one Newton step on MUFU.RSQ's square root (the round-1 kernel: +3 packed ops per pair)
 #endif
@@ -263,6 +270,265 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
     if (bad && p.status) atomicOr(p.status, kStatusNonFinite);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Stream kernel, sample-packed form (SUHPE_K2L_PACK_SAMPLES): a thread owns TWO samples in the halves of its packed
+// registers and walks the grid one point at a time per half.  Against the point-packed form above this makes the grid
+// value the broadcast scalar operand of every packed FMA (one register read less in the dot product AND in the nine
+// M sums -- the three-register-pair form runs at 2/3 rate, probe variant 8), halves the LDS per (sample, point) pair
+// and needs no lo/hi merge at the folds.  The parked per-sample state doubles, so the grid stays in shared memory in
+// chunks (two for the 4608-point grid).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kS2Threads = 512;
+constexpr int kS2Slots = kParkSlots + 1;          // + the exponent offset in force
+constexpr int kS2Chunk = ((227 * 1024 - kS2Slots * kS2Threads * 2 * 4) / 36) & ~3;   // grid points per smem chunk
+
+// q of the running maximum n = max(-q^2) a sample has seen, exactly as a grid point with that n would compute it
+__device__ __forceinline__ float q_of(float n) { return -(n * mufu_rsqrt(-n)); }
+
+constexpr float kLazyRescale = 32.0f;      // the offset follows the running minimum of q only in steps of at least this much
+
+template <bool GRAD>
+__device__ __forceinline__ void park_fold2(float* park, PackedSums& s) {
+    constexpr int kStride = 2 * kS2Threads;               // park[slot * kStride + half]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float off = park[23 * kStride + h];         // the offset the sums in registers are scaled by
+        const float sc = mufu_ex2((off - park[11 * kStride + h]) * kLog2e);        // first fold: 2^-inf = 0
+        float v[2];
+        upk(s.z, v[0], v[1]); park[h] = fmaf(park[h], sc, v[h]);
+        if (GRAD) {
+            upk(s.c, v[0], v[1]); park[kStride + h] = fmaf(park[kStride + h], sc, v[h]);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                upk(s.m[i], v[0], v[1]);
+                park[(2 + i) * kStride + h] = fmaf(park[(2 + i) * kStride + h], sc, v[h]);
+            }
+        }
+        park[11 * kStride + h] = off;
+    }
+    s.z = pk(0.f, 0.f);
+    if (GRAD) {
+        s.c = pk(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s.m[i] = pk(0.f, 0.f);
+    }
+}
+
+// the sums of NP grid points for the two samples, written phase by phase over the NP points so that the 2*NP MUFU
+// results of a phase are in flight together (four warps per scheduler do not hide a serial RSQ -> EX2 chain).
+// EDGE = some n is above -eps (clamp it, mask its gradient: clamp_min passes the gradient where input >= min);
+// otherwise every n is below the running maximum, itself <= -eps, and rs holds 1/q computed before the branch.
+template <bool GRAD, bool EDGE, int NP>
+__device__ __forceinline__ void sample_pair_sums(f2* t, f2* rs, const float* r, f2 qminLpk, PackedSums& s) {
+    bool live[NP][2];
+    if (EDGE) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float n0, n1;
+            upk(t[p], n0, n1);
+            live[p][0] = n0 <= -kLapEps; live[p][1] = n1 <= -kLapEps;
+            n0 = fminf(n0, -kLapEps); n1 = fminf(n1, -kLapEps);
+            t[p] = pk(n0, n1);
+            rs[p] = pk(mufu_rsqrt(-n0), mufu_rsqrt(-n1));
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) t[p] = fma2(mul2(t[p], rs[p]), dup(kLog2e), qminLpk);   // (-q + qmin) log2 e
+    f2 w[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        float e0, e1;
+        upk(t[p], e0, e1);
+        w[p] = pk(mufu_ex2(e0), mufu_ex2(e1));
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        w[p] = mul2(w[p], rs[p]);                                         // exp(p - c) / (-p)
+        if (GRAD) rs[p] = fma2(rs[p], rs[p], rs[p]);                      // 1/q + 1/q^2
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc_add2(s.z, w[p]);
+    if (GRAD) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            w[p] = mul2(w[p], rs[p]);
+            if (EDGE) {
+                float c0, c1;
+                upk(w[p], c0, c1);
+                w[p] = pk(live[p][0] ? c0 : 0.0f, live[p][1] ? c1 : 0.0f);
+            }
+            acc_add2(s.c, w[p]);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) acc_fma2(s.m[i], w[p], dup(r[9 * p + i]));
+    }
+}
+
+// NP grid points (r: NP*9 scalars) against the thread's two samples.  The sums carry exp(-q + off): off is an
+// exponent offset, not necessarily the running minimum of q -- any value that keeps the terms inside the fp32 range
+// gives the same sums after the final log.  It is moved only when a point undercuts it by kLazyRescale (terms then
+// stay below e^32 / q^3 < 2^84), and thr[h] is that condition expressed on n = -q^2, capped at -eps: ONE comparison
+// per sample and trip decides "rescale the sums" and "a point needs the clamp", and the common path carries no clamp,
+// no mask and no min/max per point.  (A new minimum of q itself turns up in some lane of a warp on almost half of the
+// trips; an offset change in about one trip in twenty.)
+template <bool GRAD, int NP>
+__device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const float* r, PackedSums& s, float* thr, f2& offLpk,
+                                                   float* park) {
+    f2 t[NP], rs[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) t[p] = fma2(Apk[0], dup(r[9 * p]), nTpk);
+#pragma unroll
+    for (int i = 1; i < 9; ++i)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) t[p] = fma2(Apk[i], dup(r[9 * p + i]), t[p]);
+    float nmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        float n0, n1;
+        upk(t[p], n0, n1);
+        rs[p] = pk(mufu_rsqrt(-n0), mufu_rsqrt(-n1));                     // speculative: right unless a clamp is needed
+        nmax[0] = fmaxf(nmax[0], n0); nmax[1] = fmaxf(nmax[1], n1);
+    }
+    bool edge = false;
+    if (nmax[0] > thr[0] || nmax[1] > thr[1]) {
+        float oldL[2], newL[2];
+        upk(offLpk, oldL[0], oldL[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            newL[h] = oldL[h];
+            if (nmax[h] > thr[h]) {
+                const float off = q_of(fminf(nmax[h], -kLapEps));
+                const float lim = fmaxf(off - kLazyRescale, 0.0f);
+                thr[h] = -fmaxf(lim * lim, kLapEps);                      // any n above -eps trips it
+                newL[h] = off * kLog2e;
+                park[23 * 2 * kS2Threads + h] = off;
+            }
+        }
+        const f2 sc = pk(mufu_ex2(newL[0] - oldL[0]), mufu_ex2(newL[1] - oldL[1]));   // first trip: 2^-inf = 0
+        s.z = mul2(s.z, sc);
+        if (GRAD) {
+            s.c = mul2(s.c, sc);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s.m[i] = mul2(s.m[i], sc);
+        }
+        offLpk = pk(newL[0], newL[1]);
+        edge = nmax[0] > -kLapEps || nmax[1] > -kLapEps;
+    }
+    if (edge) sample_pair_sums<GRAD, true, NP>(t, rs, r, offLpk, s);      // next to never
+    else      sample_pair_sums<GRAD, false, NP>(t, rs, r, offLpk, s);
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(kS2Threads, 1)
+laplace_stream2_kernel(LaplaceArgs p, int chunk) {
+    extern __shared__ __align__(16) float gp[];      // [chunk][9]: grid points in their natural order
+    constexpr int kStride = 2 * kS2Threads;
+    float* park = gp + (size_t)chunk * 9 + 2 * threadIdx.x;              // park[slot * kStride + half]
+    const long long tiles = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
+    const bool single_chunk = p.N <= chunk;
+    bool bad = false;
+
+    auto load_chunk = [&](int c0, int cn) {
+        const float* src = p.grid + (size_t)c0 * 9;
+        for (int i = threadIdx.x; i < cn * 9; i += kS2Threads) gp[i] = __ldg(src + i);
+    };
+    if (single_chunk) { load_chunk(0, p.N); __syncthreads(); }
+
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long sample0 = tile * (2 * kS2Threads) + 2 * threadIdx.x;
+        const bool valid[2] = {sample0 < p.n, sample0 + 1 < p.n};
+        f2 Apk[9], nTpk;
+        {
+            float A[2][9], Tf[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float Rs[9];
+                double Td;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) A[h][i] = valid[h] ? __ldg(p.A + (sample0 + h) * 9 + i) : ((i % 4 == 0) ? 1.f : 0.f);
+                if (!laplace_setup(A[h], Rs, &Td) && valid[h]) bad = true;
+                Tf[h] = (float)Td;
+#pragma unroll
+                for (int i = 0; i < 11; ++i) park[i * kStride + h] = 0.f;
+                park[11 * kStride + h] = INFINITY;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) park[(12 + i) * kStride + h] = Rs[i];
+                park[21 * kStride + h] = __int_as_float(__double2loint(Td));
+                park[22 * kStride + h] = __int_as_float(__double2hiint(Td));
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Apk[i] = pk(A[0][i], A[1][i]);
+            nTpk = pk(-Tf[0], -Tf[1]);
+        }
+        float thr[2] = {-INFINITY, -INFINITY};
+        f2 offLpk = pk(INFINITY, INFINITY);
+        PackedSums s;
+        s.z = s.c = pk(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s.m[i] = pk(0.f, 0.f);
+
+        for (int c0 = 0; c0 < p.N; c0 += chunk) {
+            const int cn = min(chunk, p.N - c0);
+            if (!single_chunk) { __syncthreads(); load_chunk(c0, cn); __syncthreads(); }
+            const int groups = cn >> 2;                       // 4 points = 36 floats = 9 float4
+            const float4* g4 = reinterpret_cast<const float4*>(gp);
+            for (int g0 = 0; g0 < groups; g0 += 32) {         // fold into the totals every 128 points
+                const int g1 = min(g0 + 32, groups);
+#pragma unroll 1
+                for (int g = g0; g < g1; ++g) {
+                    float r[36];
+#pragma unroll
+                    for (int v = 0; v < 9; ++v) {
+                        const float4 x = g4[g * 9 + v];
+                        r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                    }
+                    sample_pair_points<GRAD, 4>(Apk, nTpk, r, s, thr, offLpk, park);
+                }
+                park_fold2<GRAD>(park, s);
+            }
+            if (groups * 4 < cn) {                            // up to 3 trailing points
+                for (int k = groups * 4; k < cn; ++k) {
+                    float r[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) r[i] = gp[k * 9 + i];
+                    sample_pair_points<GRAD, 1>(Apk, nTpk, r, s, thr, offLpk, park);
+                }
+                park_fold2<GRAD>(park, s);
+            }
+        }
+
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!valid[h]) continue;
+            const long long sample = sample0 + h;
+            float A[9], Rg[9], Rs[9], grad[9], nll, logF;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { float lo, hi; upk(Apk[i], lo, hi); A[i] = h ? hi : lo; }
+            LaplaceAccum a;
+            a.qmin = park[11 * kStride + h]; a.Z = park[h]; a.C = park[kStride + h];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { a.M[i] = park[(2 + i) * kStride + h]; Rs[i] = park[(12 + i) * kStride + h]; }
+            const double Td = __hiloint2double(__float_as_int(park[22 * kStride + h]), __float_as_int(park[21 * kStride + h]));
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rg[i] = __ldg(p.Rgt + sample * 9 + i);
+            laplace_finish(a, laplace_gt_gap(A, Rg, Td), Rs, Rg, p.N, &nll, &logF, grad);
+            p.nll[sample] = nll;
+            if (p.logF) p.logF[sample] = logF;
+            if (p.mode) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) p.mode[sample * 9 + i] = Rs[i];
+            }
+            if (p.grad) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) p.grad[sample * 9 + i] = grad[i];
+            }
+        }
+    }
+    if (bad && p.status) atomicOr(p.status, kStatusNonFinite);
+}
+
 template <int L>
 __global__ void __launch_bounds__(kLapThreads)
 laplace_kernel(LaplaceArgs p, int chunk, int stride) {
@@ -366,6 +632,20 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     const int sms = device_sm_count();
     const bool per_thread = p.n >= (long long)sms * kLapThreads;
     cudaError_t err;
+#if SUHPE_K2L_PACK_SAMPLES
+    if (p.n >= (long long)sms * 2 * kS2Threads) {     // enough samples for one 1024-sample tile per SM
+        const int chunk = p.N < kS2Chunk ? ((p.N + 3) & ~3) : (p.N <= 2 * kS2Chunk ? ((((p.N + 1) / 2) + 3) & ~3) : kS2Chunk);
+        const size_t smem = ((size_t)chunk * 9 + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
+        auto kernel = p.grad ? laplace_stream2_kernel<true> : laplace_stream2_kernel<false>;
+        constexpr size_t kSmemMax = ((size_t)kS2Chunk * 9 + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
+        static unsigned long long attr_done2[2] = {0ull, 0ull};
+        err = allow_dynamic_smem(kernel, kSmemMax, attr_done2[p.grad ? 1 : 0]);
+        if (err != cudaSuccess) return err;
+        const long long tiles = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
+        const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
+        kernel<<<blocks, kS2Threads, smem, stream>>>(p, chunk);
+    } else
+#endif
     if (per_thread) {
         const int chunk = p.N < kStreamChunk ? ((p.N + 3) & ~3) : kStreamChunk;
         const size_t smem = ((size_t)chunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);

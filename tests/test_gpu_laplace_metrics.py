@@ -77,6 +77,45 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
     assert_close(tri["nll"].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "chunked grid")
 
 
+def test_laplace_sample_packed_path(cuda, golden):
+    """>= 1024 samples per SM switch to the kernel that keeps two samples per thread (odd n: the last thread's
+    second sample is a dummy).  It must agree with the warp-per-sample decomposition and the oracle, on grids whose
+    size is not a multiple of 4 (trailing points), smaller than one trip, and larger than two shared-memory chunks,
+    and on the clamp edge (every grid point within eps of the mode: A = 0 and A ~ 1e-9)."""
+    from semiuhpe_b200 import _ops
+    g = golden("laplace")
+    grids = torch.from_numpy(g["grids"]).to(cuda)
+    sms = torch.cuda.get_device_properties(cuda).multi_processor_count
+    n = sms * 1024 + 77
+    gen = torch.Generator().manual_seed(12)
+    A = (5 * torch.randn(n, 3, 3, generator=gen))
+    A[:8] = 0.0
+    A[8:16] *= 2e-10
+    A[16:32] *= 10.0                        # sharp: the offset moves several times over the grid
+    A = A.to(cuda)
+    R = random_rotations(n, gen).to(cuda)
+    big = _ops.laplace_nll(A, R, grids, grad=True, mode=True)
+    small = _ops.laplace_nll(A[:300], R[:300], grids, grad=True, mode=True)
+    assert torch.isfinite(big["nll"]).all() and torch.isfinite(big["grad"]).all()
+    assert_close(big["nll"][:300].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "decompositions")
+    assert grad_rel_err(big["grad"][16:300].cpu().numpy(), small["grad"][16:].cpu().numpy()).max() < 2e-4
+    assert (big["grad"][:16] - small["grad"][:16]).abs().max().item() < 1e-3 * small["grad"][:16].abs().max().item() + 1e-6
+    assert (big["mode"][16:300] - small["mode"][16:]).abs().max().item() < 1e-6
+    fwd = _ops.laplace_nll(A, R, grids, grad=False, mode=True)
+    assert_close(fwd["nll"].cpu().numpy(), big["nll"].cpu().numpy(), 5e-7, 2e-6, "forward-only")
+    idx = torch.cat([torch.arange(0, 32), torch.arange(n - 33, n)])
+    ref, _ = orc.laplace_nll("RLaplace", A[idx].cpu(), R[idx].cpu(), torch.from_numpy(g["grids"]))
+    assert_close(big["nll"][idx].cpu().numpy(), ref.numpy(), LAP_RTOL, LAP_ATOL, "edge and tail rows")
+    for N in (3, 5, 4607, 4608 * 3 + 2):
+        sub = torch.cat([grids] * 4)[:N].contiguous()
+        a = _ops.laplace_nll(A, R, sub, grad=True)
+        b = _ops.laplace_nll(A[:200], R[:200], sub, grad=True)
+        assert_close(a["nll"][:200].cpu().numpy(), b["nll"].cpu().numpy(), 1e-5, 1e-5, f"grid of {N} points")
+        assert grad_rel_err(a["grad"][16:200].cpu().numpy(), b["grad"][16:].cpu().numpy()).max() < 2e-4
+        last, _ = orc.laplace_nll("RLaplace", A[-7:].cpu(), R[-7:].cpu(), sub.cpu())    # 7 rows: no grid has 7 points
+        assert_close(a["nll"][-7:].cpu().numpy(), last.numpy(), LAP_RTOL, LAP_ATOL, f"tail rows, grid of {N} points")
+
+
 def test_metrics_golden(cuda, golden):
     from semiuhpe_b200.agent import compute_err_deg_from_matrices, eval_rotation_metrics
     from semiuhpe_b200.utils import compute_euler_angles_from_rotation_matrices as euler
