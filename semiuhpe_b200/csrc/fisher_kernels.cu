@@ -111,7 +111,6 @@ __device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%
 __device__ __forceinline__ void upk(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 dup(float x) { return pk(x, x); }
 __device__ __forceinline__ f2 ex22(f2 a) { float lo, hi; upk(a, lo, hi); return pk(mufu_ex2(lo), mufu_ex2(hi)); }
 
@@ -279,12 +278,6 @@ __device__ __forceinline__ void quad_run(unsigned tab, int lane, int lim32, uint
     float lo, hi;
     upk(accY, lo, hi); Y = fmaf(scale, lo + hi, Y);
     upk(accUY, lo, hi); UY = fmaf(scale, lo + hi, UY);
-}
-
-__device__ __forceinline__ float warp_sum(float x) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(kFull, x, off);
-    return x;
 }
 
 // node i's constants read back from the pair-interleaved table columns (edge nodes, phase 1)

@@ -48,7 +48,6 @@ __device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%
 __device__ __forceinline__ void upk(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 dup(float x) { return pk(x, x); }
 
 #ifndef SUHPE_K2L_THREADS
@@ -289,22 +288,22 @@ constexpr float kLazyRescale = 32.0f;      // the offset follows the running min
 
 template <bool GRAD>
 __device__ __forceinline__ void park_fold2(float* park, PackedSums& s) {
-    constexpr int kStride = 2 * kS2Threads;               // park[slot * kStride + half]
+    constexpr int kStride = 2 * kS2Threads;               // park[slot * kStride + half * kS2Threads]
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float off = park[23 * kStride + h];         // the offset the sums in registers are scaled by
-        const float sc = mufu_ex2((off - park[11 * kStride + h]) * kLog2e);        // first fold: 2^-inf = 0
+        const float off = park[23 * kStride + h * kS2Threads];         // the offset the sums in registers are scaled by
+        const float sc = mufu_ex2((off - park[11 * kStride + h * kS2Threads]) * kLog2e);        // first fold: 2^-inf = 0
         float v[2];
-        upk(s.z, v[0], v[1]); park[h] = fmaf(park[h], sc, v[h]);
+        upk(s.z, v[0], v[1]); park[h * kS2Threads] = fmaf(park[h * kS2Threads], sc, v[h]);
         if (GRAD) {
-            upk(s.c, v[0], v[1]); park[kStride + h] = fmaf(park[kStride + h], sc, v[h]);
+            upk(s.c, v[0], v[1]); park[kStride + h * kS2Threads] = fmaf(park[kStride + h * kS2Threads], sc, v[h]);
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
                 upk(s.m[i], v[0], v[1]);
-                park[(2 + i) * kStride + h] = fmaf(park[(2 + i) * kStride + h], sc, v[h]);
+                park[(2 + i) * kStride + h * kS2Threads] = fmaf(park[(2 + i) * kStride + h * kS2Threads], sc, v[h]);
             }
         }
-        park[11 * kStride + h] = off;
+        park[11 * kStride + h * kS2Threads] = off;
     }
     s.z = pk(0.f, 0.f);
     if (GRAD) {
@@ -392,7 +391,12 @@ __device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const
         nmax[0] = fmaxf(nmax[0], n0); nmax[1] = fmaxf(nmax[1], n1);
     }
     bool edge = false;
-    if (nmax[0] > thr[0] || nmax[1] > thr[1]) {
+    // forward-only launches take the branch warp-uniformly: the block is correct for the lanes that did not ask for
+    // it (their factor is 2^0) and a uniform branch needs no reconvergence barrier around the trip (-3 %; with the
+    // gradient sums in the loop the divergent form measures 1 % faster, profiles/r02w_ab_k2l_uniform.txt)
+    bool moved = nmax[0] > thr[0] || nmax[1] > thr[1];
+    if (!GRAD) moved = __any_sync(kFull, moved);
+    if (moved) {
         float oldL[2], newL[2];
         upk(offLpk, oldL[0], oldL[1]);
 #pragma unroll
@@ -403,7 +407,7 @@ __device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const
                 const float lim = fmaxf(off - kLazyRescale, 0.0f);
                 thr[h] = -fmaxf(lim * lim, kLapEps);                      // any n above -eps trips it
                 newL[h] = off * kLog2e;
-                park[23 * 2 * kS2Threads + h] = off;
+                park[23 * 2 * kS2Threads + h * kS2Threads] = off;
             }
         }
         const f2 sc = pk(mufu_ex2(newL[0] - oldL[0]), mufu_ex2(newL[1] - oldL[1]));   // first trip: 2^-inf = 0
@@ -416,6 +420,7 @@ __device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const
         offLpk = pk(newL[0], newL[1]);
         edge = nmax[0] > -kLapEps || nmax[1] > -kLapEps;
     }
+    if (!GRAD) edge = __any_sync(kFull, edge);
     if (edge) sample_pair_sums<GRAD, true, NP>(t, rs, r, offLpk, s);      // next to never
     else      sample_pair_sums<GRAD, false, NP>(t, rs, r, offLpk, s);
 }
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(kS2Threads, 1)
 laplace_stream2_kernel(LaplaceArgs p, int chunk) {
     extern __shared__ __align__(16) float gp[];      // [chunk][9]: grid points in their natural order
     constexpr int kStride = 2 * kS2Threads;
-    float* park = gp + (size_t)chunk * 9 + 2 * threadIdx.x;              // park[slot * kStride + half]
+    float* park = gp + (size_t)chunk * 9 + threadIdx.x;                  // park[slot * kStride + half * kS2Threads]: conflict-free
     const long long tiles = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
     const bool single_chunk = p.N <= chunk;
     bool bad = false;
@@ -451,12 +456,12 @@ laplace_stream2_kernel(LaplaceArgs p, int chunk) {
                 if (!laplace_setup(A[h], Rs, &Td) && valid[h]) bad = true;
                 Tf[h] = (float)Td;
 #pragma unroll
-                for (int i = 0; i < 11; ++i) park[i * kStride + h] = 0.f;
-                park[11 * kStride + h] = INFINITY;
+                for (int i = 0; i < 11; ++i) park[i * kStride + h * kS2Threads] = 0.f;
+                park[11 * kStride + h * kS2Threads] = INFINITY;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) park[(12 + i) * kStride + h] = Rs[i];
-                park[21 * kStride + h] = __int_as_float(__double2loint(Td));
-                park[22 * kStride + h] = __int_as_float(__double2hiint(Td));
+                for (int i = 0; i < 9; ++i) park[(12 + i) * kStride + h * kS2Threads] = Rs[i];
+                park[21 * kStride + h * kS2Threads] = __int_as_float(__double2loint(Td));
+                park[22 * kStride + h * kS2Threads] = __int_as_float(__double2hiint(Td));
             }
 #pragma unroll
             for (int i = 0; i < 9; ++i) Apk[i] = pk(A[0][i], A[1][i]);
@@ -507,10 +512,10 @@ laplace_stream2_kernel(LaplaceArgs p, int chunk) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) { float lo, hi; upk(Apk[i], lo, hi); A[i] = h ? hi : lo; }
             LaplaceAccum a;
-            a.qmin = park[11 * kStride + h]; a.Z = park[h]; a.C = park[kStride + h];
+            a.qmin = park[11 * kStride + h * kS2Threads]; a.Z = park[h * kS2Threads]; a.C = park[kStride + h * kS2Threads];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) { a.M[i] = park[(2 + i) * kStride + h]; Rs[i] = park[(12 + i) * kStride + h]; }
-            const double Td = __hiloint2double(__float_as_int(park[22 * kStride + h]), __float_as_int(park[21 * kStride + h]));
+            for (int i = 0; i < 9; ++i) { a.M[i] = park[(2 + i) * kStride + h * kS2Threads]; Rs[i] = park[(12 + i) * kStride + h * kS2Threads]; }
+            const double Td = __hiloint2double(__float_as_int(park[22 * kStride + h * kS2Threads]), __float_as_int(park[21 * kStride + h * kS2Threads]));
 #pragma unroll
             for (int i = 0; i < 9; ++i) Rg[i] = __ldg(p.Rgt + sample * 9 + i);
             laplace_finish(a, laplace_gt_gap(A, Rg, Td), Rs, Rg, p.N, &nll, &logF, grad);

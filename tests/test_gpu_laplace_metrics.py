@@ -92,6 +92,7 @@ def test_laplace_sample_packed_path(cuda, golden):
     A[:8] = 0.0
     A[8:16] *= 2e-10
     A[16:32] *= 10.0                        # sharp: the offset moves several times over the grid
+    A[32:48] *= 300.0                       # q up to several hundred: most terms underflow against the offset
     A = A.to(cuda)
     R = random_rotations(n, gen).to(cuda)
     big = _ops.laplace_nll(A, R, grids, grad=True, mode=True)
