@@ -35,6 +35,9 @@ namespace {
 #ifndef SUHPE_K2L_PACK_SAMPLES
 #define SUHPE_K2L_PACK_SAMPLES 1     // 0: never use the sample-packed stream kernel (A/B builds)
 #endif
+#ifndef SUHPE_K2L_DIAG_NOMUFU
+#define SUHPE_K2L_DIAG_NOMUFU 0
+#endif
 #ifndef SUHPE_K2L_NEWTON
 #define SUHPE_K2L_NEWTON 0      // 1 = one Newton step on MUFU.RSQ's square root (the round-1 kernel: +3 packed ops per pair)
 #endif
@@ -313,6 +316,14 @@ __device__ __forceinline__ void park_fold2(float* park, PackedSums& s) {
     }
 }
 
+#if SUHPE_K2L_DIAG_NOMUFU   // timing diagnostic only (wrong results): what do the 16 MUFU of a trip cost?
+__device__ __forceinline__ float s2_rsqrt(float x) { return x * -0.37f; }
+__device__ __forceinline__ float s2_ex2(float x) { return x * 0.011f; }
+#else
+__device__ __forceinline__ float s2_rsqrt(float x) { return mufu_rsqrt(x); }
+__device__ __forceinline__ float s2_ex2(float x) { return mufu_ex2(x); }
+#endif
+
 // the sums of NP grid points for the two samples, written phase by phase over the NP points so that the 2*NP MUFU
 // results of a phase are in flight together (four warps per scheduler do not hide a serial RSQ -> EX2 chain).
 // EDGE = some n is above -eps (clamp it, mask its gradient: clamp_min passes the gradient where input >= min);
@@ -328,7 +339,7 @@ __device__ __forceinline__ void sample_pair_sums(f2* t, f2* rs, const float* r, 
             live[p][0] = n0 <= -kLapEps; live[p][1] = n1 <= -kLapEps;
             n0 = fminf(n0, -kLapEps); n1 = fminf(n1, -kLapEps);
             t[p] = pk(n0, n1);
-            rs[p] = pk(mufu_rsqrt(-n0), mufu_rsqrt(-n1));
+            rs[p] = pk(s2_rsqrt(-n0), s2_rsqrt(-n1));
         }
     }
 #pragma unroll
@@ -338,7 +349,7 @@ __device__ __forceinline__ void sample_pair_sums(f2* t, f2* rs, const float* r, 
     for (int p = 0; p < NP; ++p) {
         float e0, e1;
         upk(t[p], e0, e1);
-        w[p] = pk(mufu_ex2(e0), mufu_ex2(e1));
+        w[p] = pk(s2_ex2(e0), s2_ex2(e1));
     }
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -387,7 +398,7 @@ __device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const
     for (int p = 0; p < NP; ++p) {
         float n0, n1;
         upk(t[p], n0, n1);
-        rs[p] = pk(mufu_rsqrt(-n0), mufu_rsqrt(-n1));                     // speculative: right unless a clamp is needed
+        rs[p] = pk(s2_rsqrt(-n0), s2_rsqrt(-n1));                     // speculative: right unless a clamp is needed
         nmax[0] = fmaxf(nmax[0], n0); nmax[1] = fmaxf(nmax[1], n1);
     }
     bool edge = false;
@@ -410,7 +421,7 @@ __device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const
                 park[23 * 2 * kS2Threads + h * kS2Threads] = off;
             }
         }
-        const f2 sc = pk(mufu_ex2(newL[0] - oldL[0]), mufu_ex2(newL[1] - oldL[1]));   // first trip: 2^-inf = 0
+        const f2 sc = pk(s2_ex2(newL[0] - oldL[0]), s2_ex2(newL[1] - oldL[1]));   // first trip: 2^-inf = 0
         s.z = mul2(s.z, sc);
         if (GRAD) {
             s.c = mul2(s.c, sc);
