@@ -280,9 +280,10 @@ laplace_stream_kernel(LaplaceArgs p, int chunk) {
 // and needs no lo/hi merge at the folds.  The parked per-sample state doubles, so the grid stays in shared memory in
 // chunks (two for the 4608-point grid).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kS2Threads = 512;
+constexpr int kS2Threads = 512;      // 640 threads leave 96 registers: 410 bytes of spills in the loop
 constexpr int kS2Slots = kParkSlots + 1;          // + the exponent offset in force
 constexpr int kS2Chunk = ((227 * 1024 - kS2Slots * kS2Threads * 2 * 4) / 36) & ~3;   // grid points per smem chunk
+__host__ __device__ constexpr int s2_grid_floats(int chunk) { return chunk * 9; }
 
 // q of the running maximum n = max(-q^2) a sample has seen, exactly as a grid point with that n would compute it
 __device__ __forceinline__ float q_of(float n) { return -(n * mufu_rsqrt(-n)); }
@@ -383,24 +384,28 @@ __device__ __forceinline__ void sample_pair_sums(f2* t, f2* rs, const float* r, 
 // per sample and trip decides "rescale the sums" and "a point needs the clamp", and the common path carries no clamp,
 // no mask and no min/max per point.  (A new minimum of q itself turns up in some lane of a warp on almost half of the
 // trips; an offset change in about one trip in twenty.)
-template <bool GRAD, int NP>
-__device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const float* r, PackedSums& s, float* thr, f2& offLpk,
-                                                   float* park) {
-    f2 t[NP], rs[NP];
+// dot products of NP points with the two samples, speculative 1/q (right unless a clamp is needed), the trip's max n
+template <int NP>
+__device__ __forceinline__ void stage_dots(const f2* Apk, f2 nTpk, const float* r, f2* t, f2* rs, float* nmax) {
 #pragma unroll
     for (int p = 0; p < NP; ++p) t[p] = fma2(Apk[0], dup(r[9 * p]), nTpk);
 #pragma unroll
     for (int i = 1; i < 9; ++i)
 #pragma unroll
         for (int p = 0; p < NP; ++p) t[p] = fma2(Apk[i], dup(r[9 * p + i]), t[p]);
-    float nmax[2] = {-INFINITY, -INFINITY};
+    nmax[0] = nmax[1] = -INFINITY;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         float n0, n1;
         upk(t[p], n0, n1);
-        rs[p] = pk(s2_rsqrt(-n0), s2_rsqrt(-n1));                     // speculative: right unless a clamp is needed
+        rs[p] = pk(s2_rsqrt(-n0), s2_rsqrt(-n1));
         nmax[0] = fmaxf(nmax[0], n0); nmax[1] = fmaxf(nmax[1], n1);
     }
+}
+
+// the one comparison per sample and trip; returns true when a point of the trip needs the clamp path
+template <bool GRAD>
+__device__ __forceinline__ bool offset_step(const float* nmax, PackedSums& s, float* thr, f2& offLpk, float* park) {
     bool edge = false;
     // forward-only launches take the branch warp-uniformly: the block is correct for the lanes that did not ask for
     // it (their factor is 2^0) and a uniform branch needs no reconvergence barrier around the trip (-3 %; with the
@@ -431,9 +436,20 @@ __device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const
         offLpk = pk(newL[0], newL[1]);
         edge = nmax[0] > -kLapEps || nmax[1] > -kLapEps;
     }
+    // a new minimum turns up in some lane of a warp on almost half of the trips, so that block stays small and
+    // rejoins; only the clamp (a grid point within 1e-4 rad-ish of the mode: next to never) takes the long way round
     if (!GRAD) edge = __any_sync(kFull, edge);
-    if (edge) sample_pair_sums<GRAD, true, NP>(t, rs, r, offLpk, s);      // next to never
-    else      sample_pair_sums<GRAD, false, NP>(t, rs, r, offLpk, s);
+    return edge;
+}
+
+template <bool GRAD, int NP>
+__device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const float* r, PackedSums& s, float* thr, f2& offLpk,
+                                                   float* park) {
+    f2 t[NP], rs[NP];
+    float nmax[2];
+    stage_dots<NP>(Apk, nTpk, r, t, rs, nmax);
+    if (offset_step<GRAD>(nmax, s, thr, offLpk, park)) sample_pair_sums<GRAD, true, NP>(t, rs, r, offLpk, s);      // next to never
+    else sample_pair_sums<GRAD, false, NP>(t, rs, r, offLpk, s);
 }
 
 template <bool GRAD>
@@ -441,7 +457,7 @@ __global__ void __launch_bounds__(kS2Threads, 1)
 laplace_stream2_kernel(LaplaceArgs p, int chunk) {
     extern __shared__ __align__(16) float gp[];      // [chunk][9]: grid points in their natural order
     constexpr int kStride = 2 * kS2Threads;
-    float* park = gp + (size_t)chunk * 9 + threadIdx.x;                  // park[slot * kStride + half * kS2Threads]: conflict-free
+    float* park = gp + s2_grid_floats(chunk) + threadIdx.x;              // park[slot * kStride + half * kS2Threads]: conflict-free
     const long long tiles = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
     const bool single_chunk = p.N <= chunk;
     bool bad = false;
@@ -651,9 +667,9 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
 #if SUHPE_K2L_PACK_SAMPLES
     if (p.n >= (long long)sms * 2 * kS2Threads) {     // enough samples for one 1024-sample tile per SM
         const int chunk = p.N < kS2Chunk ? ((p.N + 3) & ~3) : (p.N <= 2 * kS2Chunk ? ((((p.N + 1) / 2) + 3) & ~3) : kS2Chunk);
-        const size_t smem = ((size_t)chunk * 9 + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
+        const size_t smem = ((size_t)s2_grid_floats(chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
         auto kernel = p.grad ? laplace_stream2_kernel<true> : laplace_stream2_kernel<false>;
-        constexpr size_t kSmemMax = ((size_t)kS2Chunk * 9 + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
+        constexpr size_t kSmemMax = ((size_t)s2_grid_floats(kS2Chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
         static unsigned long long attr_done2[2] = {0ull, 0ull};
         err = allow_dynamic_smem(kernel, kSmemMax, attr_done2[p.grad ? 1 : 0]);
         if (err != cudaSuccess) return err;
