@@ -34,7 +34,7 @@ for bl, bu in ((32, 128), (5, 0), (64, 257)):
         ssl_loss(a, rot(bl))[0].backward()
 # K2L: warp kernel, point-packed stream kernel, sample-packed stream kernel (single chunk with trailing points; three chunks)
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
-for n, N in ((33, 37), (sms * 256 + 5, 37), (sms * 1024 + 3, 39), (sms * 1024 + 3, 7451)):
+for n, N in ((33, 37), (sms * 256 + 5, 37), (sms * 1024 - 3, 39), (sms * 1024 - 3, 7451)):
     A = 5 * torch.randn(n, 9, device=dev, generator=g)
     A[:4] = 0
     grid = rot(N)

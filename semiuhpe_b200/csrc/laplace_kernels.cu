@@ -33,7 +33,7 @@ namespace suhpe {
 namespace {
 
 #ifndef SUHPE_K2L_PACK_SAMPLES
-#define SUHPE_K2L_PACK_SAMPLES 1     // 0: never use the sample-packed stream kernel (A/B builds)
+#define SUHPE_K2L_PACK_SAMPLES 1     // 0 / 2: never / always use the sample-packed stream kernel for large batches (A/B builds)
 #endif
 #ifndef SUHPE_K2L_DIAG_NOMUFU
 #define SUHPE_K2L_DIAG_NOMUFU 0
@@ -665,7 +665,12 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     const bool per_thread = p.n >= (long long)sms * kLapThreads;
     cudaError_t err;
 #if SUHPE_K2L_PACK_SAMPLES
-    if (p.n >= (long long)sms * 2 * kS2Threads) {     // enough samples for one 1024-sample tile per SM
+    // Both stream kernels run whole rounds of one tile per SM: 512 samples in 0.387 ms (point-packed) or 1024 in 0.670 ms
+    // (sample-packed) on the 4608-point grid.  Take the sample-packed kernel when its rounds come out cheaper -- always
+    // from 7 x 512 samples per SM on, and below that whenever the batch does not leave its last round mostly empty.
+    const long long rounds1 = ((p.n + kStreamThreads - 1) / kStreamThreads + sms - 1) / sms;
+    const long long rounds2 = ((p.n + 2 * kS2Threads - 1) / (2 * kS2Threads) + sms - 1) / sms;
+    if (per_thread && (SUHPE_K2L_PACK_SAMPLES == 2 || rounds2 * 173 <= rounds1 * 100)) {
         const int chunk = p.N < kS2Chunk ? ((p.N + 3) & ~3) : (p.N <= 2 * kS2Chunk ? ((((p.N + 1) / 2) + 3) & ~3) : kS2Chunk);
         const size_t smem = ((size_t)s2_grid_floats(chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
         auto kernel = p.grad ? laplace_stream2_kernel<true> : laplace_stream2_kernel<false>;

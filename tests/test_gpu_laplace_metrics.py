@@ -78,15 +78,16 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
 
 
 def test_laplace_sample_packed_path(cuda, golden):
-    """>= 1024 samples per SM switch to the kernel that keeps two samples per thread (odd n: the last thread's
-    second sample is a dummy).  It must agree with the warp-per-sample decomposition and the oracle, on grids whose
+    """Large batches switch to the kernel that keeps two samples per thread (launch_laplace picks it when its rounds of
+    1024 samples per SM come out cheaper than the point-packed kernel's rounds of 512: here one round against two;
+    odd n: the last thread's second sample is a dummy).  It must agree with the warp-per-sample decomposition and the oracle, on grids whose
     size is not a multiple of 4 (trailing points), smaller than one trip, and larger than two shared-memory chunks,
     and on the clamp edge (every grid point within eps of the mode: A = 0 and A ~ 1e-9)."""
     from semiuhpe_b200 import _ops
     g = golden("laplace")
     grids = torch.from_numpy(g["grids"]).to(cuda)
     sms = torch.cuda.get_device_properties(cuda).multi_processor_count
-    n = sms * 1024 + 77
+    n = sms * 1024 - 77
     gen = torch.Generator().manual_seed(12)
     A = (5 * torch.randn(n, 3, 3, generator=gen))
     A[:8] = 0.0
