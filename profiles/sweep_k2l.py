@@ -15,8 +15,9 @@ sms = torch.cuda.get_device_properties(dev).multi_processor_count
 grid = rot(4608)
 nmax = sms * 512 * 9
 A, R = 5 * torch.randn(nmax, 9, device=dev, generator=gen), rot(nmax)
-for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 18):
-    n = sms * 256 * k
+sizes = [1024, 2048, 4096, 8192, 16384, 32768] + [sms * 256 * k for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 18)]
+for n in sizes:
+    k = n / (sms * 256)
     for _ in range(3):
         _ops.laplace_nll(A[:n], R[:n], grid, grad=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -25,4 +26,4 @@ for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 18):
         _ops.laplace_nll(A[:n], R[:n], grid, grad=True)
     e1.record()
     torch.cuda.synchronize()
-    print(f"n = {k:2d} x {sms} x 256 = {n:7d}: {e0.elapsed_time(e1) / 10:7.3f} ms", flush=True)
+    print(f"n = {k:6.2f} x {sms} x 256 = {n:7d}: {e0.elapsed_time(e1) / 10:7.3f} ms", flush=True)

@@ -23,6 +23,19 @@ for n in (32, 128, 1024, 8192):
     for _ in range(200): run()
     b.record(); torch.cuda.synchronize()
     print(f"K2 n={n:5d}: {a.elapsed_time(b) / 200 * 1e3:7.1f} us per launch (back to back)")
+from semiuhpe_b200 import _ops
+grid = _quat_to_matrix(torch.nn.functional.normalize(torch.randn(4608, 4, device=dev, generator=gen), dim=1)).contiguous()
+for n in (32, 128, 160, 1024, 8192, 32768):
+    A = 5 * torch.randn(n, 9, device=dev, generator=gen)
+    R = _quat_to_matrix(torch.nn.functional.normalize(torch.randn(n, 4, device=dev, generator=gen), dim=1)).contiguous()
+    run = lambda: _ops.laplace_nll(A, R, grid, grad=True, mode=True)
+    for _ in range(10): run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(100): run()
+    b.record(); torch.cuda.synchronize()
+    print(f"K2L n={n:5d} x 4608: {a.elapsed_time(b) / 100 * 1e3:7.1f} us per launch (back to back)")
 A32 = 10 * torch.randn(32, 9, device=dev, generator=gen)
 R32 = _quat_to_matrix(torch.nn.functional.normalize(torch.randn(32, 4, device=dev, generator=gen), dim=1)).contiguous()
 A128 = 10 * torch.randn(128, 9, device=dev, generator=gen)

@@ -15,18 +15,21 @@
 // K=9 contraction has no tensor-core shape anyway.
 //
 // Three decompositions of the same sum:
-//   stream2 thread per TWO samples (>= 1024 samples per SM): 512-thread persistent CTAs; a thread keeps its two
+//   stream2 thread per TWO samples (batches from ~4k rotations, see launch_laplace): 512-thread persistent CTAs, launched
+//           as clusters of 2-8 CTAs that slice the grid and merge through distributed shared memory when the batch has
+//           fewer 1024-sample tiles than the device has SMs; a thread keeps its two
 //           samples in the halves of packed registers and the grid point is the broadcast scalar operand, so every
 //           FMA of the loop is a packed FFMA2 in the two-register-pair form (25 packed ops and 2.25 LDS.128 per
 //           sample and 2 grid points); one comparison per sample and trip covers the clamp and the exponent offset
-//   stream  thread per sample (>= 256 samples per SM): the grid sits in shared memory as interleaved point PAIRS
-//           and the packed halves are two grid points (28 packed ops per pair of points)
+//   stream  thread per sample (>= 256 samples per SM, where its rounds of 512 fit the batch better): the grid sits in shared memory as interleaved point PAIRS
+//           and the packed halves are two grid points (25 packed ops per pair of points)
 //   warp    warp per sample (small batches): lanes stride the grid, shuffle merge
 // Both stream forms fold their block sums into the totals every 128 points so the fp32 summation error does not
 // grow with N.
 // Per-sample set-up (proper SVD, T, the ground-truth term) runs in fp64: see laplace_setup.
 #include "kernels.cuh"
 #include "so3_math.cuh"
+#include <cooperative_groups.h>
 
 namespace suhpe {
 
@@ -454,21 +457,27 @@ __device__ __forceinline__ void sample_pair_points(const f2* Apk, f2 nTpk, const
 
 template <bool GRAD>
 __global__ void __launch_bounds__(kS2Threads, 1)
-laplace_stream2_kernel(LaplaceArgs p, int chunk) {
+laplace_stream2_kernel(LaplaceArgs p, int chunk, int slices, int per_slice) {
     extern __shared__ __align__(16) float gp[];      // [chunk][9]: grid points in their natural order
     constexpr int kStride = 2 * kS2Threads;
     float* park = gp + s2_grid_floats(chunk) + threadIdx.x;              // park[slot * kStride + half * kS2Threads]: conflict-free
     const long long tiles = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
-    const bool single_chunk = p.N <= chunk;
+    // slices > 1: launched as thread-block clusters of `slices` CTAs.  The CTAs of a cluster take the same tile of
+    // samples and one slice of the grid each (per_slice points, a multiple of 4); their totals meet in the cluster's
+    // first CTA through distributed shared memory.  This is what fills the SMs when the batch has fewer tiles than that.
+    const int rank = slices > 1 ? (int)(blockIdx.x % (unsigned)slices) : 0;
+    const int first = rank * per_slice;
+    const int last = slices > 1 ? min(p.N, first + per_slice) : p.N;    // this CTA's grid points: [first, last)
+    const bool single_chunk = last - first <= chunk;
     bool bad = false;
 
     auto load_chunk = [&](int c0, int cn) {
         const float* src = p.grid + (size_t)c0 * 9;
         for (int i = threadIdx.x; i < cn * 9; i += kS2Threads) gp[i] = __ldg(src + i);
     };
-    if (single_chunk) { load_chunk(0, p.N); __syncthreads(); }
+    if (single_chunk) { load_chunk(first, max(last - first, 0)); __syncthreads(); }
 
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x / (unsigned)slices; tile < tiles; tile += gridDim.x / (unsigned)slices) {
         const long long sample0 = tile * (2 * kS2Threads) + 2 * threadIdx.x;
         const bool valid[2] = {sample0 < p.n, sample0 + 1 < p.n};
         f2 Apk[9], nTpk;
@@ -501,8 +510,8 @@ laplace_stream2_kernel(LaplaceArgs p, int chunk) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) s.m[i] = pk(0.f, 0.f);
 
-        for (int c0 = 0; c0 < p.N; c0 += chunk) {
-            const int cn = min(chunk, p.N - c0);
+        for (int c0 = first; c0 < last; c0 += chunk) {
+            const int cn = min(chunk, last - c0);
             if (!single_chunk) { __syncthreads(); load_chunk(c0, cn); __syncthreads(); }
             const int groups = cn >> 2;                       // 4 points = 36 floats = 9 float4
             const float4* g4 = reinterpret_cast<const float4*>(gp);
@@ -529,6 +538,32 @@ laplace_stream2_kernel(LaplaceArgs p, int chunk) {
                 }
                 park_fold2<GRAD>(park, s);
             }
+        }
+
+        if (slices > 1) {
+            // totals of the other slices: Z, C, M[9] and the offset they are scaled by (slots 0..11) of the same thread
+            // in the peer CTA, rebased to the smaller offset.  A slice without points reports offset +inf and zeros.
+            namespace cg = cooperative_groups;
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();
+            if (rank == 0) {
+                for (int peer = 1; peer < slices; ++peer) {
+                    const float* theirs = cluster.map_shared_rank(park, peer);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int o = h * kS2Threads;
+                        const float mine_off = park[11 * kStride + o], their_off = theirs[11 * kStride + o];
+                        const float off = fminf(mine_off, their_off);
+                        const float fm = mufu_ex2((off - mine_off) * kLog2e), ft = mufu_ex2((off - their_off) * kLog2e);
+#pragma unroll
+                        for (int i = 0; i < (GRAD ? 11 : 1); ++i)
+                            park[i * kStride + o] = fmaf(park[i * kStride + o], fm, theirs[i * kStride + o] * ft);
+                        park[11 * kStride + o] = off;
+                    }
+                }
+            }
+            cluster.sync();                                   // the peers' parked state stays in place until it has been read
+            if (rank != 0) continue;
         }
 
 #pragma unroll
@@ -665,23 +700,75 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     const bool per_thread = p.n >= (long long)sms * kLapThreads;
     cudaError_t err;
 #if SUHPE_K2L_PACK_SAMPLES
-    // Both stream kernels run whole rounds of one tile per SM: 512 samples in 0.387 ms (point-packed) or 1024 in 0.670 ms
-    // (sample-packed) on the 4608-point grid.  Take the sample-packed kernel when its rounds come out cheaper -- always
-    // from 7 x 512 samples per SM on, and below that whenever the batch does not leave its last round mostly empty.
-    const long long rounds1 = ((p.n + kStreamThreads - 1) / kStreamThreads + sms - 1) / sms;
-    const long long rounds2 = ((p.n + 2 * kS2Threads - 1) / (2 * kS2Threads) + sms - 1) / sms;
-    if (per_thread && (SUHPE_K2L_PACK_SAMPLES == 2 || rounds2 * 173 <= rounds1 * 100)) {
-        const int chunk = p.N < kS2Chunk ? ((p.N + 3) & ~3) : (p.N <= 2 * kS2Chunk ? ((((p.N + 1) / 2) + 3) & ~3) : kS2Chunk);
-        const size_t smem = ((size_t)s2_grid_floats(chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
+    {
+        // Which decomposition?  Estimated cost in units of one sample-packed tile (1024 samples against the whole
+        // grid: 0.67 ms for 4608 points), from the timings in profiles/r02af_k2l_batch_sweep.txt:
+        //   point-packed stream kernel   0.58 per round of 512 samples per SM (only from 256 samples per SM on)
+        //   warp kernel                  0.03 + 4.0e-5 per sample (small batches)
+        //   sample-packed kernel         1/C + 0.02 + 0.007 C per round of clusters, C CTAs sharing a tile and slicing
+        //                                the grid (every CTA of a cluster repeats the per-sample set-up of the tile)
+        // The clusters are what fills the SMs when the batch has fewer than one tile per SM, and what trims the last,
+        // mostly empty round of a larger one.
+        const long long tiles2 = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
+        const long long rounds1 = ((p.n + kStreamThreads - 1) / kStreamThreads + sms - 1) / sms;
         auto kernel = p.grad ? laplace_stream2_kernel<true> : laplace_stream2_kernel<false>;
         constexpr size_t kSmemMax = ((size_t)s2_grid_floats(kS2Chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
         static unsigned long long attr_done2[2] = {0ull, 0ull};
         err = allow_dynamic_smem(kernel, kSmemMax, attr_done2[p.grad ? 1 : 0]);
         if (err != cudaSuccess) return err;
-        const long long tiles = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
-        const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
-        kernel<<<blocks, kS2Threads, smem, stream>>>(p, chunk);
-    } else
+        double best = per_thread ? 0.58 * (double)rounds1 : 0.03 + 4.0e-5 * (double)p.n;
+        int best_slices = 0, best_per = 0, best_chunk = 0;
+        long long best_clusters = 0;
+        for (int c = 1; c <= 8; c *= 2) {
+            const int per = c == 1 ? p.N : (((p.N + c - 1) / c + 3) & ~3);
+            if (c > 1 && (per < 64 || (long long)(c - 1) * per >= p.N)) break;         // slices too thin, or an empty one
+            const int chunk = per < kS2Chunk ? ((per + 3) & ~3) : (per <= 2 * kS2Chunk ? ((((per + 1) / 2) + 3) & ~3) : kS2Chunk);
+            long long clusters = sms;
+            if (c > 1) {
+                // how many clusters of c such CTAs fit the device at once (they must share a GPC): asked once per
+                // (device, kernel, c) for the largest footprint
+                static int fit[64][2][4];
+                int dev = 0;
+                cudaGetDevice(&dev);
+                int& cached = fit[dev & 63][p.grad ? 1 : 0][c == 2 ? 1 : c == 4 ? 2 : 3];
+                if (cached == 0) {
+                    cudaLaunchConfig_t q = {};
+                    q.gridDim = dim3((unsigned)(c * sms), 1, 1);
+                    q.blockDim = dim3(kS2Threads, 1, 1);
+                    q.dynamicSmemBytes = kSmemMax;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    q.attrs = at; q.numAttrs = 1;
+                    int m = 0;
+                    if (cudaOccupancyMaxActiveClusters(&m, kernel, &q) != cudaSuccess) { (void)cudaGetLastError(); m = 0; }
+                    cached = m > 0 ? m : -1;
+                }
+                if (cached < 0) continue;
+                clusters = cached;
+            }
+            const long long rounds = (tiles2 + clusters - 1) / clusters;
+            const double cost = (double)rounds * (1.0 / c + (c > 1 ? 0.02 + 0.007 * c : 0.0));
+            if (cost < best || (SUHPE_K2L_PACK_SAMPLES == 2 && best_slices == 0)) {     // 2: always one of the sample-packed forms
+                best = cost; best_slices = c; best_per = per; best_chunk = chunk;
+                best_clusters = tiles2 < clusters ? tiles2 : clusters;
+            }
+        }
+        if (best_slices > 0) {
+            const size_t smem = ((size_t)s2_grid_floats(best_chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3((unsigned)(best_clusters * best_slices), 1, 1);
+            q.blockDim = dim3(kS2Threads, 1, 1);
+            q.dynamicSmemBytes = smem;
+            q.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)best_slices; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = best_slices > 1 ? 1 : 0;
+            err = cudaLaunchKernelEx(&q, kernel, p, best_chunk, best_slices, best_per);
+            return err != cudaSuccess ? err : cudaGetLastError();
+        }
+    }
 #endif
     if (per_thread) {
         const int chunk = p.N < kStreamChunk ? ((p.N + 3) & ~3) : kStreamChunk;

@@ -77,17 +77,20 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
     assert_close(tri["nll"].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "chunked grid")
 
 
-def test_laplace_sample_packed_path(cuda, golden):
+@pytest.mark.parametrize("batch", ["one_round", "8k", "33k", "90k"])
+def test_laplace_sample_packed_path(cuda, golden, batch):
     """Large batches switch to the kernel that keeps two samples per thread (launch_laplace picks it when its rounds of
-    1024 samples per SM come out cheaper than the point-packed kernel's rounds of 512: here one round against two;
-    odd n: the last thread's second sample is a dummy).  It must agree with the warp-per-sample decomposition and the oracle, on grids whose
-    size is not a multiple of 4 (trailing points), smaller than one trip, and larger than two shared-memory chunks,
-    and on the clamp edge (every grid point within eps of the mode: A = 0 and A ~ 1e-9)."""
+    1024 samples per SM come out cheaper than the other decompositions'; odd n: the last thread's second sample is a
+    dummy).  Mid-sized batches run it as thread-block CLUSTERS: the CTAs of a cluster share a tile of samples, take a
+    slice of the grid each and merge their totals through distributed shared memory (8k: 8 slices, 33k: 4, 90k: 2 on a
+    148-SM part).  Every form must agree with the warp-per-sample decomposition and the oracle, on grids whose size is
+    not a multiple of 4 (trailing points), smaller than one trip (no clusters then), and larger than two shared-memory
+    chunks, and on the clamp edge (every grid point within eps of the mode: A = 0 and A ~ 1e-10)."""
     from semiuhpe_b200 import _ops
     g = golden("laplace")
     grids = torch.from_numpy(g["grids"]).to(cuda)
     sms = torch.cuda.get_device_properties(cuda).multi_processor_count
-    n = sms * 1024 - 77
+    n = {"one_round": sms * 1024 - 77, "8k": 8191, "33k": 33001, "90k": 90001}[batch]
     gen = torch.Generator().manual_seed(12)
     A = (5 * torch.randn(n, 3, 3, generator=gen))
     A[:8] = 0.0
@@ -108,7 +111,7 @@ def test_laplace_sample_packed_path(cuda, golden):
     idx = torch.cat([torch.arange(0, 32), torch.arange(n - 33, n)])
     ref, _ = orc.laplace_nll("RLaplace", A[idx].cpu(), R[idx].cpu(), torch.from_numpy(g["grids"]))
     assert_close(big["nll"][idx].cpu().numpy(), ref.numpy(), LAP_RTOL, LAP_ATOL, "edge and tail rows")
-    for N in (3, 5, 4607, 4608 * 3 + 2):
+    for N in (3, 5, 130, 4607, 4608 * 3 + 2):
         sub = torch.cat([grids] * 4)[:N].contiguous()
         a = _ops.laplace_nll(A, R, sub, grad=True)
         b = _ops.laplace_nll(A[:200], R[:200], sub, grad=True)
