@@ -32,10 +32,10 @@ for bl, bu in ((32, 128), (5, 0), (64, 257)):
             ssl_loss(a, rot(bl), w, st, -4.0, type_unsuper=unsup, aug_rot_mat=rot(bu))[0].backward()
     else:
         ssl_loss(a, rot(bl))[0].backward()
-# K2L: warp kernel, point-packed stream kernel, sample-packed stream kernel (single chunk with trailing points; three chunks),
+# K2L: CTA-per-sample kernel, warp kernel, point-packed stream kernel, sample-packed stream kernel (single chunk with trailing points; three chunks),
 # and the sample-packed kernel as clusters of 8 / 4 / 2 CTAs that slice the grid and merge through distributed shared memory
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
-for n, N in ((33, 37), (sms * 256 + 5, 37), (sms * 1024 - 3, 39), (sms * 1024 - 3, 7451), (8191, 4608), (8191, 13826), (33001, 130), (90001, 4607)):
+for n, N in ((33, 37), (33, 4608), (700, 37), (sms * 256 + 5, 37), (sms * 1024 - 3, 39), (sms * 1024 - 3, 7451), (8191, 4608), (8191, 13826), (33001, 130), (90001, 4607)):
     A = 5 * torch.randn(n, 9, device=dev, generator=g)
     A[:4] = 0
     grid = rot(N)

@@ -14,7 +14,7 @@
 // FP32 FMA only: the reference forbids TF32 here (rotation_laplace.py:13), and a
 // K=9 contraction has no tensor-core shape anyway.
 //
-// Three decompositions of the same sum:
+// Four decompositions of the same sum:
 //   stream2 thread per TWO samples (batches from ~4k rotations, see launch_laplace): 512-thread persistent CTAs, launched
 //           as clusters of 2-8 CTAs that slice the grid and merge through distributed shared memory when the batch has
 //           fewer 1024-sample tiles than the device has SMs; a thread keeps its two
@@ -23,7 +23,8 @@
 //           sample and 2 grid points); one comparison per sample and trip covers the clamp and the exponent offset
 //   stream  thread per sample (>= 256 samples per SM, where its rounds of 512 fit the batch better): the grid sits in shared memory as interleaved point PAIRS
 //           and the packed halves are two grid points (25 packed ops per pair of points)
-//   warp    warp per sample (small batches): lanes stride the grid, shuffle merge
+//   warp    warp per sample (up to a few thousand samples): grid in shared memory, lanes stride it, shuffle merge
+//   block   CTA per sample (training-sized batches): lanes stride the grid in L2, shuffle + shared-memory merge
 // Both stream forms fold their block sums into the totals every 128 points so the fp32 summation error does not
 // grow with N.
 // Per-sample set-up (proper SVD, T, the ground-truth term) runs in fp64: see laplace_setup.
@@ -40,6 +41,9 @@ namespace {
 #endif
 #ifndef SUHPE_K2L_DIAG_NOMUFU
 #define SUHPE_K2L_DIAG_NOMUFU 0
+#endif
+#ifndef SUHPE_K2L_BLOCK_KERNEL
+#define SUHPE_K2L_BLOCK_KERNEL 512    // batches up to this many samples take the CTA-per-sample kernel (0: never)
 #endif
 #ifndef SUHPE_K2L_NEWTON
 #define SUHPE_K2L_NEWTON 0      // 1 = one Newton step on MUFU.RSQ's square root (the round-1 kernel: +3 packed ops per pair)
@@ -691,6 +695,81 @@ laplace_kernel(LaplaceArgs p, int chunk, int stride) {
     if (bad && p.status) atomicOr(p.status, kStatusNonFinite);
 }
 
+// Block kernel (training-sized batches, a few hundred samples at most): one 256-thread CTA per sample, the lanes stride
+// the grid straight out of global memory (it is L2-resident after the first CTA; staging 166 KB of it in shared memory
+// per CTA, as the warp kernel does, costs more than the whole sum at this size), warp partials merge by shuffle and the
+// eight warps through 384 bytes of shared memory.
+__global__ void __launch_bounds__(kLapThreads)
+laplace_block_kernel(LaplaceArgs p) {
+    __shared__ float part[kLapThreads / 32][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool bad = false;
+    for (long long sample = blockIdx.x; sample < p.n; sample += gridDim.x) {
+        float A[9], Rs[9];
+        double Td;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A[i] = __ldg(p.A + sample * 9 + i);
+        if (!laplace_setup(A, Rs, &Td)) bad = true;
+        const float T = (float)Td;
+        LaplaceAccum a;
+        laplace_accum_init(a);
+        for (int k = threadIdx.x; k < p.N; k += kLapThreads) {
+            float r[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) r[i] = __ldg(p.grid + (size_t)k * 9 + i);
+            laplace_accum_point(a, A, T, r);
+        }
+        laplace_accum_flush(a);
+        auto warp_merge = [&]() {            // the lanes' partial sums under their common minimum
+            float qg = a.qmin;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) qg = fminf(qg, __shfl_xor_sync(kFull, qg, off));
+            laplace_accum_rebase(a, qg);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                a.Z += __shfl_xor_sync(kFull, a.Z, off);
+                a.C += __shfl_xor_sync(kFull, a.C, off);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) a.M[i] += __shfl_xor_sync(kFull, a.M[i], off);
+            }
+        };
+        warp_merge();
+        if (lane == 0) {
+            part[warp][0] = a.qmin; part[warp][1] = a.Z; part[warp][2] = a.C;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) part[warp][3 + i] = a.M[i];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            laplace_accum_init(a);
+            if (lane < kLapThreads / 32) {
+                a.qmin = part[lane][0]; a.Z = part[lane][1]; a.C = part[lane][2];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) a.M[i] = part[lane][3 + i];
+            }
+            warp_merge();
+            if (lane == 0) {
+                float Rg[9], grad[9], nll, logF;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rg[i] = __ldg(p.Rgt + sample * 9 + i);
+                laplace_finish(a, laplace_gt_gap(A, Rg, Td), Rs, Rg, p.N, &nll, &logF, grad);
+                p.nll[sample] = nll;
+                if (p.logF) p.logF[sample] = logF;
+                if (p.mode) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) p.mode[sample * 9 + i] = Rs[i];
+                }
+                if (p.grad) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) p.grad[sample * 9 + i] = grad[i];
+                }
+            }
+        }
+        __syncthreads();                     // part[] is rewritten by the next sample
+    }
+    if (bad && p.status && threadIdx.x == 0) atomicOr(p.status, kStatusNonFinite);
+}
+
 }  // namespace
 
 cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
@@ -699,6 +778,13 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     const int sms = device_sm_count();
     const bool per_thread = p.n >= (long long)sms * kLapThreads;
     cudaError_t err;
+#if SUHPE_K2L_BLOCK_KERNEL
+    if (p.n <= (long long)SUHPE_K2L_BLOCK_KERNEL) {
+        const unsigned blocks = (unsigned)(p.n < 4ll * sms ? p.n : 4ll * sms);
+        laplace_block_kernel<<<blocks, kLapThreads, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+#endif
 #if SUHPE_K2L_PACK_SAMPLES
     {
         // Which decomposition?  Estimated cost in units of one sample-packed tile (1024 samples against the whole

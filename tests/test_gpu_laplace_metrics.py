@@ -77,20 +77,22 @@ def test_laplace_large_batch_path_matches_small(cuda, golden):
     assert_close(tri["nll"].cpu().numpy(), small["nll"].cpu().numpy(), 1e-5, 1e-5, "chunked grid")
 
 
-@pytest.mark.parametrize("batch", ["one_round", "8k", "33k", "90k"])
+@pytest.mark.parametrize("batch", ["one_round", "1500", "8k", "33k", "90k"])
 def test_laplace_sample_packed_path(cuda, golden, batch):
     """Large batches switch to the kernel that keeps two samples per thread (launch_laplace picks it when its rounds of
     1024 samples per SM come out cheaper than the other decompositions'; odd n: the last thread's second sample is a
     dummy).  Mid-sized batches run it as thread-block CLUSTERS: the CTAs of a cluster share a tile of samples, take a
     slice of the grid each and merge their totals through distributed shared memory (8k: 8 slices, 33k: 4, 90k: 2 on a
-    148-SM part).  Every form must agree with the warp-per-sample decomposition and the oracle, on grids whose size is
+    148-SM part); 1,501 rotations take the warp-per-sample kernel (grid staged in shared memory), and the 200-300 row
+    calls they are all compared with take the CTA-per-sample kernel that training-sized batches use (the one the golden
+    vectors pin).  Every form must agree with that one and the oracle, on grids whose size is
     not a multiple of 4 (trailing points), smaller than one trip (no clusters then), and larger than two shared-memory
     chunks, and on the clamp edge (every grid point within eps of the mode: A = 0 and A ~ 1e-10)."""
     from semiuhpe_b200 import _ops
     g = golden("laplace")
     grids = torch.from_numpy(g["grids"]).to(cuda)
     sms = torch.cuda.get_device_properties(cuda).multi_processor_count
-    n = {"one_round": sms * 1024 - 77, "8k": 8191, "33k": 33001, "90k": 90001}[batch]
+    n = {"one_round": sms * 1024 - 77, "1500": 1501, "8k": 8191, "33k": 33001, "90k": 90001}[batch]
     gen = torch.Generator().manual_seed(12)
     A = (5 * torch.randn(n, 3, 3, generator=gen))
     A[:8] = 0.0
