@@ -619,6 +619,10 @@ def side_configs(torch, dev, _ops, fp32_peak_tflops, hbm_peak_gbs, with_cpu=True
     out["c3_roofline"] = {"bound": "fp32", "achieved": out["c3_laplace_tflops_at_230400_flop"], "peak": fp32_peak_tflops,
                           "unit": "TFLOP/s", "frac": out["c3_laplace_tflops_at_230400_flop"] / fp32_peak_tflops,
                           "algorithmic_flop_per_rotation": 230400}
+    # the same call at other batch sizes: training-sized (CTA-per-sample kernel), mid-sized (thread-block clusters that
+    # slice the grid and merge through distributed shared memory)
+    for nb, reps in ((160, 200), (8192, 50), (32768, 20)):
+        out[f"c3_laplace_n{nb}_N4608_us"] = 1e3 * timed(lambda: _ops.laplace_nll(A3[:nb], R3[:nb], grid, grad=True, mode=True), reps)
     n4 = 10_000_000
     Rp, Rg = rot(n4), rot(n4)
     ge = (torch.rand(n4, 3, device=dev, generator=gen) * 2 - 1) * 89
