@@ -1,5 +1,6 @@
 """K2L fwd+bwd time against the batch size (4608-point grid): python profiles/sweep_k2l.py  -- used to check launch_laplace's choice
-between the point-packed and the sample-packed stream kernels (builds with -DSUHPE_K2L_PACK_SAMPLES=0 / 1 / 2)."""
+between the warp kernel and the stream kernel's plain and cluster forms (r02ae / r02af: builds with -DSUHPE_K2L_PACK_SAMPLES=0 / 1 / 2 while the
+round-1 point-packed stream kernel was still in the tree; now -DSUHPE_K2L_FORCE_STREAM=1 forces the stream kernel)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -14,19 +14,16 @@
 // FP32 FMA only: the reference forbids TF32 here (rotation_laplace.py:13), and a
 // K=9 contraction has no tensor-core shape anyway.
 //
-// Four decompositions of the same sum:
-//   stream2 thread per TWO samples (batches from ~4k rotations, see launch_laplace): 512-thread persistent CTAs, launched
-//           as clusters of 2-8 CTAs that slice the grid and merge through distributed shared memory when the batch has
-//           fewer 1024-sample tiles than the device has SMs; a thread keeps its two
+// Three decompositions of the same sum, picked by launch_laplace:
+//   stream  thread per TWO samples (batches from ~4k rotations): 512-thread persistent CTAs; a thread keeps its two
 //           samples in the halves of packed registers and the grid point is the broadcast scalar operand, so every
 //           FMA of the loop is a packed FFMA2 in the two-register-pair form (25 packed ops and 2.25 LDS.128 per
-//           sample and 2 grid points); one comparison per sample and trip covers the clamp and the exponent offset
-//   stream  thread per sample (>= 256 samples per SM, where its rounds of 512 fit the batch better): the grid sits in shared memory as interleaved point PAIRS
-//           and the packed halves are two grid points (25 packed ops per pair of points)
+//           sample and 2 grid points); one comparison per sample and trip covers the clamp and the exponent offset;
+//           block sums fold into the totals every 128 points so the fp32 summation error does not grow with N.
+//           Launched as thread-block clusters of 2-8 CTAs that slice the grid and merge through distributed shared
+//           memory when the batch has fewer 1024-sample tiles than the device has SMs
 //   warp    warp per sample (up to a few thousand samples): grid in shared memory, lanes stride it, shuffle merge
 //   block   CTA per sample (training-sized batches): lanes stride the grid in L2, shuffle + shared-memory merge
-// Both stream forms fold their block sums into the totals every 128 points so the fp32 summation error does not
-// grow with N.
 // Per-sample set-up (proper SVD, T, the ground-truth term) runs in fp64: see laplace_setup.
 #include "kernels.cuh"
 #include "so3_math.cuh"
@@ -36,17 +33,14 @@ namespace suhpe {
 
 namespace {
 
-#ifndef SUHPE_K2L_PACK_SAMPLES
-#define SUHPE_K2L_PACK_SAMPLES 1     // 0 / 2: never / always use the sample-packed stream kernel for large batches (A/B builds)
+#ifndef SUHPE_K2L_FORCE_STREAM
+#define SUHPE_K2L_FORCE_STREAM 0     // 1: always one of the stream kernel's forms, whatever the batch size (A/B builds)
 #endif
 #ifndef SUHPE_K2L_DIAG_NOMUFU
 #define SUHPE_K2L_DIAG_NOMUFU 0
 #endif
 #ifndef SUHPE_K2L_BLOCK_KERNEL
 #define SUHPE_K2L_BLOCK_KERNEL 512    // batches up to this many samples take the CTA-per-sample kernel (0: never)
-#endif
-#ifndef SUHPE_K2L_NEWTON
-#define SUHPE_K2L_NEWTON 0      // 1 = one Newton step on MUFU.RSQ's square root (the round-1 kernel: +3 packed ops per pair)
 #endif
 constexpr int kLapThreads = 256;
 constexpr int kGridChunk = 4608;           // grid points resident in shared memory at once
@@ -60,12 +54,8 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 dup(float x) { return pk(x, x); }
 
-#ifndef SUHPE_K2L_THREADS
-#define SUHPE_K2L_THREADS 512
-#endif
-constexpr int kStreamThreads = SUHPE_K2L_THREADS;
 
-// block sums of the packed loop: lo half = even grid points, hi half = odd
+// block sums of the packed loop: lo / hi half = the thread's first / second sample
 struct PackedSums { f2 z, c, m[9]; };
 
 // accumulate in place: pins every accumulator to one register pair for the whole loop (without
@@ -73,215 +63,11 @@ struct PackedSums { f2 z, c, m[9]; };
 __device__ __forceinline__ void acc_add2(f2& acc, f2 y) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(y)); }
 __device__ __forceinline__ void acc_fma2(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 
-template <bool GRAD>
-__device__ __forceinline__ void packed_scale(PackedSums& s, float sc) {
-    const f2 k = dup(sc);
-    s.z = mul2(s.z, k);
-    if (!GRAD) return;
-    s.c = mul2(s.c, k);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) s.m[i] = mul2(s.m[i], k);
-}
-
-// One pair of grid points, first half: nq = -q = -sqrt(max(T - <A,R_k>, eps)) for both points and
-// rs = 1/q, live = (d >= eps).  Everything is carried NEGATED (nd = t - T, nq = nd * rs), which
-// makes the Newton step and the exponent plain FFMA2s with no sign flips:
-//   ne = nq*nq + nd = q^2 - d,   nq' = nq + (rs/2) ne,   exponent = (qmin - q) log2e = nq' log2e + qmin log2e
-// Same arithmetic per point as laplace_accum_point / sqrt_pair (negation is exact).
-struct PairRoots { f2 nq, rs; bool live0, live1; };
-
-__device__ __forceinline__ PairRoots packed_roots(const float* A, float T, const f2* r) {
-    // -T rides in the first FMA's addend: nd = <A,R_k> - T in nine packed ops
-    f2 t = fma2(dup(A[0]), r[0], dup(-T));
-#pragma unroll
-    for (int i = 1; i < 9; ++i) t = fma2(dup(A[i]), r[i], t);
-    float n0, n1;
-    upk(t, n0, n1);
-    PairRoots o;
-    o.live0 = n0 <= -kLapEps; o.live1 = n1 <= -kLapEps;        // clamp_min passes the gradient where input >= min
-    n0 = fminf(n0, -kLapEps); n1 = fminf(n1, -kLapEps);
-    const f2 nd = pk(n0, n1);
-    o.rs = pk(mufu_rsqrt(-n0), mufu_rsqrt(-n1));
-    const f2 nq = mul2(nd, o.rs);
-#if SUHPE_K2L_NEWTON
-    o.nq = fma2(mul2(o.rs, dup(0.5f)), fma2(nq, nq, nd), nq);
-#else
-    // q = d * rsqrt(d) as MUFU.RSQ delivers it (<= 2^-22.4 relative): the exponent (qmin - q) log2(e) moves by
-    // < 4e-6 for q <= 20, the weights by the same relative amount -- an order of magnitude below the
-    // reference's own fp32 noise on this path -- and the Newton step's three packed ops per
-    // point pair (11 % of the loop's FMA-pipe work) are not spent
-    o.nq = nq;
-#endif
-    return o;
-}
-
-// second half: weights and sums, relative to the running minimum held as qminL = qmin * log2e
-template <bool GRAD>
-__device__ __forceinline__ void packed_sums(PackedSums& s, const PairRoots& o, float qminL, const f2* r) {
-    float e0, e1;
-    upk(fma2(o.nq, dup(kLog2e), dup(qminL)), e0, e1);
-    const f2 w = mul2(pk(mufu_ex2(e0), mufu_ex2(e1)), o.rs);   // exp(p - c) / (-p)
-    acc_add2(s.z, w);
-    if (!GRAD) return;                                         // forward only: the normaliser sum alone
-    float c0, c1;
-    upk(mul2(w, fma2(o.rs, o.rs, o.rs)), c0, c1);               // w (1/q + 1/q^2)
-    const f2 cw = pk(o.live0 ? c0 : 0.0f, o.live1 ? c1 : 0.0f);
-    acc_add2(s.c, cw);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) acc_fma2(s.m[i], cw, r[i]);
-}
-
-// Per-thread state that is touched once per 128 grid points (or once per sample) is parked in
-// shared memory behind the grid, [slot][thread], so the hot loop keeps its registers for the 22
-// packed block sums and the grid operands:
-//   slots 0-10  totals Z, C, M[9], expressed relative to slot 11 = the running minimum they were
-//               last folded at (the block sums are relative to the CURRENT minimum; the fold rescales)
-//   slots 12-20 mode R*,  slots 21-22 the fp64 trace T
-constexpr int kParkSlots = 23;
-constexpr int kStreamChunk = ((227 * 1024 - kParkSlots * kStreamThreads * 4) / 36) & ~3;   // grid points per smem chunk
-
-template <bool GRAD>
-__device__ __forceinline__ void park_fold(float* park, PackedSums& s, float qmin) {
-    const float sc = mufu_ex2((qmin - park[11 * kStreamThreads]) * kLog2e);    // first fold: 2^-inf = 0
-    float lo, hi;
-    upk(s.z, lo, hi); park[0] = fmaf(park[0], sc, lo + hi); s.z = pk(0.f, 0.f);
-    if (!GRAD) { park[11 * kStreamThreads] = qmin; return; }
-    upk(s.c, lo, hi); park[kStreamThreads] = fmaf(park[kStreamThreads], sc, lo + hi); s.c = pk(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        upk(s.m[i], lo, hi);
-        park[(2 + i) * kStreamThreads] = fmaf(park[(2 + i) * kStreamThreads], sc, lo + hi);
-        s.m[i] = pk(0.f, 0.f);
-    }
-    park[11 * kStreamThreads] = qmin;
-}
-
-// GRAD = false: forward-only calls (no gradient requested: validation under no_grad) skip the eleven
-// gradient sums per point pair -- 17 packed ops instead of 28.
-template <bool GRAD>
-__global__ void __launch_bounds__(kStreamThreads, 1)
-laplace_stream_kernel(LaplaceArgs p, int chunk) {
-    extern __shared__ __align__(16) float gp[];      // [chunk/2][9][2]: point pairs interleaved per component
-    float* park = gp + (size_t)chunk * 9 + threadIdx.x;
-    const long long tiles = (p.n + kStreamThreads - 1) / kStreamThreads;
-    const bool single_chunk = p.N <= chunk;
-    bool bad = false;
-
-    auto load_chunk = [&](int c0, int cn) {
-        const float* src = p.grid + (size_t)c0 * 9;
-        for (int i = threadIdx.x; i < cn * 9; i += kStreamThreads) {
-            const int k = i / 9, ij = i - 9 * k;
-            gp[(k >> 1) * 18 + 2 * ij + (k & 1)] = __ldg(src + i);
-        }
-    };
-    if (single_chunk) { load_chunk(0, p.N); __syncthreads(); }
-
-
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long sample = tile * kStreamThreads + threadIdx.x;
-        const bool valid = sample < p.n;
-        float A[9], T;
-        {
-            float Rs[9];
-            double Td;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) A[i] = valid ? __ldg(p.A + sample * 9 + i) : ((i % 4 == 0) ? 1.f : 0.f);
-            if (!laplace_setup(A, Rs, &Td) && valid) bad = true;
-            T = (float)Td;
-#pragma unroll
-            for (int i = 0; i < 11; ++i) park[i * kStreamThreads] = 0.f;
-            park[11 * kStreamThreads] = INFINITY;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) park[(12 + i) * kStreamThreads] = Rs[i];
-            park[21 * kStreamThreads] = __int_as_float(__double2loint(Td));
-            park[22 * kStreamThreads] = __int_as_float(__double2hiint(Td));
-        }
-
-        float qmin = INFINITY, qminL = INFINITY;              // running minimum of q and qmin * log2e
-        PackedSums s;
-        s.z = s.c = pk(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) s.m[i] = pk(0.f, 0.f);
-
-        for (int c0 = 0; c0 < p.N; c0 += chunk) {
-            const int cn = min(chunk, p.N - c0);
-            if (!single_chunk) { __syncthreads(); load_chunk(c0, cn); __syncthreads(); }
-            const int groups = cn >> 2;                       // 4 points = 2 pairs = 9 float4
-            const float4* g4 = reinterpret_cast<const float4*>(gp);
-            for (int g0 = 0; g0 < groups; g0 += 32) {         // fold into the totals every 128 points
-                const int g1 = min(g0 + 32, groups);
-#pragma unroll 1
-                for (int g = g0; g < g1; ++g) {
-                    f2 r[18];
-#pragma unroll
-                    for (int v = 0; v < 9; ++v) {
-                        const float4 x = g4[g * 9 + v];
-                        r[2 * v] = pk(x.x, x.y); r[2 * v + 1] = pk(x.z, x.w);
-                    }
-                    // roots of all four points first, ONE running-minimum check per group (the
-                    // rescale is rare), then the weights: the two pairs are independent
-                    // straight-line chains the scheduler can interleave
-                    const PairRoots o0 = packed_roots(A, T, r);
-                    const PairRoots o1 = packed_roots(A, T, r + 9);
-                    float a0, a1, b0, b1;
-                    upk(o0.nq, a0, a1); upk(o1.nq, b0, b1);
-                    const float qm = -fmaxf(fmaxf(a0, a1), fmaxf(b0, b1));
-                    if (qm < qmin) {                          // new running maximum of p = -q
-                        packed_scale<GRAD>(s, mufu_ex2((qm - qmin) * kLog2e));
-                        qmin = qm;
-                        qminL = qm * kLog2e;
-                    }
-                    packed_sums<GRAD>(s, o0, qminL, r);
-                    packed_sums<GRAD>(s, o1, qminL, r + 9);
-                }
-                park_fold<GRAD>(park, s, qmin);
-            }
-            if (groups * 4 < cn) {                            // up to 3 trailing points: scalar path, then merged
-                LaplaceAccum ta;
-                laplace_accum_init(ta);
-                for (int k = groups * 4; k < cn; ++k) {
-                    float r[9];
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) r[i] = gp[(k >> 1) * 18 + 2 * i + (k & 1)];
-                    laplace_accum_point(ta, A, T, r);
-                }
-                if (ta.qmin < qmin) qmin = ta.qmin; else laplace_accum_scale(ta, mufu_ex2((qmin - ta.qmin) * kLog2e));
-                qminL = qmin * kLog2e;
-                s.z = pk(ta.z, 0.f); s.c = pk(ta.c, 0.f);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) s.m[i] = pk(ta.m[i], 0.f);
-                park_fold<GRAD>(park, s, qmin);
-            }
-        }
-
-        if (valid) {
-            float Rg[9], Rs[9], grad[9], nll, logF;
-            LaplaceAccum a;
-            a.qmin = qmin; a.Z = park[0]; a.C = park[kStreamThreads];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) { a.M[i] = park[(2 + i) * kStreamThreads]; Rs[i] = park[(12 + i) * kStreamThreads]; }
-            const double Td = __hiloint2double(__float_as_int(park[22 * kStreamThreads]), __float_as_int(park[21 * kStreamThreads]));
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Rg[i] = __ldg(p.Rgt + sample * 9 + i);
-            laplace_finish(a, laplace_gt_gap(A, Rg, Td), Rs, Rg, p.N, &nll, &logF, grad);
-            p.nll[sample] = nll;
-            if (p.logF) p.logF[sample] = logF;
-            if (p.mode) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) p.mode[sample * 9 + i] = Rs[i];
-            }
-            if (p.grad) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) p.grad[sample * 9 + i] = grad[i];
-            }
-        }
-    }
-    if (bad && p.status) atomicOr(p.status, kStatusNonFinite);
-}
+constexpr int kParkSlots = 23;       // per-sample state parked in shared memory: Z, C, M[9], offset, R*[9], T (fp64)
 
 // ---------------------------------------------------------------------------------------------------
-// Stream kernel, sample-packed form (SUHPE_K2L_PACK_SAMPLES): a thread owns TWO samples in the halves of its packed
-// registers and walks the grid one point at a time per half.  Against the point-packed form above this makes the grid
+// Stream kernel: a thread owns TWO samples in the halves of its packed registers and walks the grid one point at a
+// time per half.  Against the round-1 form (two grid POINTS in the halves, one sample per thread) this makes the grid
 // value the broadcast scalar operand of every packed FMA (one register read less in the dot product AND in the nine
 // M sums -- the three-register-pair form runs at 2/3 rate, probe variant 8), halves the LDS per (sample, point) pair
 // and needs no lo/hi merge at the folds.  The parked per-sample state doubles, so the grid stays in shared memory in
@@ -776,33 +562,30 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     if (p.N <= 0) return cudaErrorInvalidValue;
     const int sms = device_sm_count();
-    const bool per_thread = p.n >= (long long)sms * kLapThreads;
     cudaError_t err;
 #if SUHPE_K2L_BLOCK_KERNEL
-    if (p.n <= (long long)SUHPE_K2L_BLOCK_KERNEL) {
+    if (!SUHPE_K2L_FORCE_STREAM && p.n <= (long long)SUHPE_K2L_BLOCK_KERNEL) {
         const unsigned blocks = (unsigned)(p.n < 4ll * sms ? p.n : 4ll * sms);
         laplace_block_kernel<<<blocks, kLapThreads, 0, stream>>>(p);
         return cudaGetLastError();
     }
 #endif
-#if SUHPE_K2L_PACK_SAMPLES
     {
-        // Which decomposition?  Estimated cost in units of one sample-packed tile (1024 samples against the whole
-        // grid: 0.67 ms for 4608 points), from the timings in profiles/r02af_k2l_batch_sweep.txt:
-        //   point-packed stream kernel   0.58 per round of 512 samples per SM (only from 256 samples per SM on)
-        //   warp kernel                  0.03 + 4.0e-5 per sample (small batches)
-        //   sample-packed kernel         1/C + 0.02 + 0.007 C per round of clusters, C CTAs sharing a tile and slicing
-        //                                the grid (every CTA of a cluster repeats the per-sample set-up of the tile)
+        // Which decomposition?  Estimated cost in units of one stream-kernel tile (1024 samples against the whole grid:
+        // 0.67 ms for 4608 points), from the timings in profiles/r02af_k2l_batch_sweep.txt:
+        //   warp kernel      0.03 + 4.0e-5 per sample (up to 256 samples per SM)
+        //   stream kernel    1/C + 0.02 + 0.007 C per round of clusters, C CTAs sharing a tile and slicing the grid
+        //                    (every CTA of a cluster repeats the per-sample set-up of the tile); C = 1: plain launch
         // The clusters are what fills the SMs when the batch has fewer than one tile per SM, and what trims the last,
         // mostly empty round of a larger one.
-        const long long tiles2 = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
-        const long long rounds1 = ((p.n + kStreamThreads - 1) / kStreamThreads + sms - 1) / sms;
+        const long long tiles = (p.n + 2 * kS2Threads - 1) / (2 * kS2Threads);
         auto kernel = p.grad ? laplace_stream2_kernel<true> : laplace_stream2_kernel<false>;
         constexpr size_t kSmemMax = ((size_t)s2_grid_floats(kS2Chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
         static unsigned long long attr_done2[2] = {0ull, 0ull};
         err = allow_dynamic_smem(kernel, kSmemMax, attr_done2[p.grad ? 1 : 0]);
         if (err != cudaSuccess) return err;
-        double best = per_thread ? 0.58 * (double)rounds1 : 0.03 + 4.0e-5 * (double)p.n;
+        const bool warp_allowed = !SUHPE_K2L_FORCE_STREAM && p.n < (long long)sms * kLapThreads;
+        double best = 0.03 + 4.0e-5 * (double)p.n;
         int best_slices = 0, best_per = 0, best_chunk = 0;
         long long best_clusters = 0;
         for (int c = 1; c <= 8; c *= 2) {
@@ -833,11 +616,11 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
                 if (cached < 0) continue;
                 clusters = cached;
             }
-            const long long rounds = (tiles2 + clusters - 1) / clusters;
+            const long long rounds = (tiles + clusters - 1) / clusters;
             const double cost = (double)rounds * (1.0 / c + (c > 1 ? 0.02 + 0.007 * c : 0.0));
-            if (cost < best || (SUHPE_K2L_PACK_SAMPLES == 2 && best_slices == 0)) {     // 2: always one of the sample-packed forms
+            if (cost < best || (!warp_allowed && best_slices == 0)) {
                 best = cost; best_slices = c; best_per = per; best_chunk = chunk;
-                best_clusters = tiles2 < clusters ? tiles2 : clusters;
+                best_clusters = tiles < clusters ? tiles : clusters;
             }
         }
         if (best_slices > 0) {
@@ -855,27 +638,14 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
             return err != cudaSuccess ? err : cudaGetLastError();
         }
     }
-#endif
-    if (per_thread) {
-        const int chunk = p.N < kStreamChunk ? ((p.N + 3) & ~3) : kStreamChunk;
-        const size_t smem = ((size_t)chunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);
-        auto kernel = p.grad ? laplace_stream_kernel<true> : laplace_stream_kernel<false>;
-        // allowed once per device at the largest size any call can ask for
-        constexpr size_t kSmemMax = ((size_t)kStreamChunk * 9 + (size_t)kParkSlots * kStreamThreads) * sizeof(float);
-        static unsigned long long attr_done[2] = {0ull, 0ull};
-        err = allow_dynamic_smem(kernel, kSmemMax, attr_done[p.grad ? 1 : 0]);
-        if (err != cudaSuccess) return err;
-        const long long tiles = (p.n + kStreamThreads - 1) / kStreamThreads;
-        const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);    // one persistent CTA per SM
-        kernel<<<blocks, kStreamThreads, smem, stream>>>(p, chunk);
-    } else {
+    {
         const int chunk = p.N < kGridChunk ? p.N : kGridChunk;
         const int stride = (chunk + 3) & ~3;
         const size_t smem = (size_t)9 * stride * sizeof(float);
         static unsigned long long attr_done32 = 0ull;
         err = allow_dynamic_smem(laplace_kernel<32>, (size_t)9 * kGridChunk * sizeof(float), attr_done32);
         if (err != cudaSuccess) return err;
-        // spread the samples over all SMs: up to 8 per block pass, as few as 1 when the batch is tiny
+        // spread the samples over the SMs, 8 per block pass
         const long long tiles = (p.n + (kLapThreads / 32) - 1) / (kLapThreads / 32);
         const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
         laplace_kernel<32><<<blocks, kLapThreads, smem, stream>>>(p, chunk, stride);
