@@ -635,6 +635,16 @@ cudaError_t launch_laplace(LaplaceArgs p, cudaStream_t stream) {
             at[0].val.clusterDim.x = (unsigned)best_slices; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             q.attrs = at; q.numAttrs = best_slices > 1 ? 1 : 0;
             err = cudaLaunchKernelEx(&q, kernel, p, best_chunk, best_slices, best_per);
+            if (err != cudaSuccess && best_slices > 1) {
+                // the cluster launch was refused (a partitioned or busy device can fit fewer clusters than the occupancy
+                // query promised): run the same kernel unclustered, one tile per CTA against the whole grid
+                (void)cudaGetLastError();
+                const int chunk = p.N < kS2Chunk ? ((p.N + 3) & ~3) : (p.N <= 2 * kS2Chunk ? ((((p.N + 1) / 2) + 3) & ~3) : kS2Chunk);
+                q.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms), 1, 1);
+                q.dynamicSmemBytes = ((size_t)s2_grid_floats(chunk) + (size_t)kS2Slots * kS2Threads * 2) * sizeof(float);
+                q.numAttrs = 0;
+                err = cudaLaunchKernelEx(&q, kernel, p, chunk, 1, p.N);
+            }
             return err != cudaSuccess ? err : cudaGetLastError();
         }
     }
