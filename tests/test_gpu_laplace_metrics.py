@@ -123,6 +123,53 @@ def test_laplace_sample_packed_path(cuda, golden, batch):
         assert_close(a["nll"][-7:].cpu().numpy(), last.numpy(), LAP_RTOL, LAP_ATOL, f"tail rows, grid of {N} points")
 
 
+def test_laplace_launches_in_a_cuda_graph(cuda, golden):
+    """Every K2L form is a plain stream-ordered launch (the cluster forms through cudaLaunchKernelEx): captured in a
+    CUDA graph after one eager call, replayed on new inputs, bit-identical to the eager result."""
+    import semiuhpe_b200
+    from semiuhpe_b200.laplace.rotation_laplace import NLL_loss
+    g = golden("laplace")
+    grids = torch.from_numpy(g["grids"]).to(cuda)
+    gen = torch.Generator().manual_seed(77)
+    semiuhpe_b200.set_error_checking(False)
+    try:
+        for n in (160, 1501, 8191, 40001):           # block / warp / clusters of 8 / clusters of 2-4
+            A = (5 * torch.randn(n, 3, 3, generator=gen)).to(cuda)
+            R = random_rotations(n, gen).to(cuda)
+            sA, sR = torch.empty_like(A), torch.empty_like(R)
+            leaf = sA.requires_grad_(True)
+            out = {}
+
+            def step():
+                leaf.grad = None
+                losses, mode = NLL_loss("RLaplace", leaf, sR, grids)
+                losses.sum().backward()
+                out["nll"], out["mode"] = losses.detach(), mode
+
+            with torch.no_grad():
+                sA.copy_(A + 1.0); sR.copy_(R)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            with torch.no_grad():
+                sA.copy_(A); sR.copy_(R)
+            graph.replay()
+            torch.cuda.synchronize()
+            got = (out["nll"].clone(), out["mode"].clone(), leaf.grad.clone())
+            l2 = A.clone().requires_grad_(True)
+            ref, mode = NLL_loss("RLaplace", l2, R, grids)
+            ref.sum().backward()
+            assert torch.equal(got[0], ref.detach()) and torch.equal(got[1], mode) and torch.equal(got[2], l2.grad), n
+    finally:
+        semiuhpe_b200.set_error_checking(True)
+
+
 def test_metrics_golden(cuda, golden):
     from semiuhpe_b200.agent import compute_err_deg_from_matrices, eval_rotation_metrics
     from semiuhpe_b200.utils import compute_euler_angles_from_rotation_matrices as euler
