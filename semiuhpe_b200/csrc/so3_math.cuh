@@ -89,7 +89,11 @@ SUHPE_HD float sqrt_rn(float a) {
 // so rank-deficient input (A = 0 gives U = V = R = I like LAPACK) is safe.
 // ----------------------------------------------------------------------------
 constexpr int kJacobiSweeps = 5;          // fp32: converged to rounding for every tested spectrum
-constexpr int kJacobiSweepsF64 = 7;       // fp64 (K2L only): two more quadratic sweeps reach 1e-16
+constexpr int kJacobiSweepsF64 = 7;       // fp64 from scratch: two more quadratic sweeps reach 1e-16
+constexpr int kJacobiPolishF64 = 2;       // fp64 sweeps on top of a converged fp32 run (K2L set-up; one already reaches 5e-13 on T)
+#ifndef SUHPE_K2L_SETUP_F64_ONLY
+#define SUHPE_K2L_SETUP_F64_ONLY 0
+#endif
 
 // scalar-type shims so the same source instantiates in fp32 (every kernel) and fp64 (K2L's
 // per-sample set-up, where the Laplace NLL cancels sum(s) against <A,R>)
@@ -148,8 +152,11 @@ SUHPE_HD void rot_swap(bool doit, T* bp, T* bq, T* vp, T* vq, T& np_, T& nq_) {
 
 // A (fp32 input), U, V row-major 3x3 in T.  Returns false when A holds a non-finite value
 // (the reference's torch.svd raises in that case).
+// Vstart (nullable, row-major, fp32): an orthogonal matrix to start the one-sided iteration from -- the V of a
+// lower-precision run of the same routine, which leaves `sweeps` only the polishing to do.
 template <typename T>
-SUHPE_HD bool proper_svd3_t(const float* A, T* U, T* V, T* s) {
+SUHPE_HD bool proper_svd3_t(const float* A, T* U, T* V, T* s, const float* Vstart = nullptr,
+                            int sweeps = (sizeof(T) == 8 ? kJacobiSweepsF64 : kJacobiSweeps)) {
     constexpr bool kF64 = sizeof(T) == 8;
     float amax = 0.0f;
 #pragma unroll
@@ -179,9 +186,29 @@ SUHPE_HD bool proper_svd3_t(const float* A, T* U, T* V, T* s) {
     T b1[3] = {T(A[1] * down), T(A[4] * down), T(A[7] * down)};
     T b2[3] = {T(A[2] * down), T(A[5] * down), T(A[8] * down)};
     T v0[3] = {T(1), T(0), T(0)}, v1[3] = {T(0), T(1), T(0)}, v2[3] = {T(0), T(0), T(1)};
+    if (Vstart) {
+        // start from A V0 instead of A: V0 = Vstart made orthogonal to the working precision by one Newton-Schulz
+        // step, V0 = Vs (3 I - Vs^T Vs) / 2 (Vs is orthogonal to fp32 rounding: the step squares that error)
+        const T c0[3] = {T(Vstart[0]), T(Vstart[3]), T(Vstart[6])}, c1[3] = {T(Vstart[1]), T(Vstart[4]), T(Vstart[7])},
+                c2[3] = {T(Vstart[2]), T(Vstart[5]), T(Vstart[8])};
+        auto dot = [](const T* x, const T* y) { return fma_t(x[0], y[0], fma_t(x[1], y[1], x[2] * y[2])); };
+        const T g00 = dot(c0, c0), g11 = dot(c1, c1), g22 = dot(c2, c2), g01 = dot(c0, c1), g02 = dot(c0, c2), g12 = dot(c1, c2);
+        const T m00 = T(1.5) - T(0.5) * g00, m11 = T(1.5) - T(0.5) * g11, m22 = T(1.5) - T(0.5) * g22;
+        const T m01 = T(-0.5) * g01, m02 = T(-0.5) * g02, m12 = T(-0.5) * g12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            v0[i] = fma_t(c0[i], m00, fma_t(c1[i], m01, c2[i] * m02));
+            v1[i] = fma_t(c0[i], m01, fma_t(c1[i], m11, c2[i] * m12));
+            v2[i] = fma_t(c0[i], m02, fma_t(c1[i], m12, c2[i] * m22));
+        }
+        const T a0[3] = {b0[0], b1[0], b2[0]}, a1[3] = {b0[1], b1[1], b2[1]}, a2[3] = {b0[2], b1[2], b2[2]};   // rows of A
+        b0[0] = dot(a0, v0); b0[1] = dot(a1, v0); b0[2] = dot(a2, v0);
+        b1[0] = dot(a0, v1); b1[1] = dot(a1, v1); b1[2] = dot(a2, v1);
+        b2[0] = dot(a0, v2); b2[1] = dot(a1, v2); b2[2] = dot(a2, v2);
+    }
     const T skip = kF64 ? T(1e-32) : T(1e-16f);
 #pragma unroll 1
-    for (int sweep = 0; sweep < (kF64 ? kJacobiSweepsF64 : kJacobiSweeps); ++sweep) {
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
         jacobi_pair(b0, b1, v0, v1, skip);
         jacobi_pair(b0, b2, v0, v2, skip);
         jacobi_pair(b1, b2, v1, v2, skip);
@@ -253,7 +280,15 @@ SUHPE_HD void u_diag_vt(const float* U, const float* V, float d0, float d1, floa
 // rounding for the cost of one 3x3 Jacobi per sample (the grid loop is ~5,000x more work).
 SUHPE_HD bool laplace_setup(const float* A, float* Rs, double* T) {
     double U[9], V[9], s[3];
+#if SUHPE_K2L_SETUP_F64_ONLY
     const bool ok = proper_svd3_t<double>(A, U, V, s);
+#else
+    // the fp32 iteration (K1's) finds V to fp32 rounding at a fraction of the cost of fp64 sweeps (two sqrt and two
+    // divisions per rotation); kJacobiPolishF64 fp64 sweeps from there converge quadratically: 1e-7 -> 1e-14 -> 1e-28
+    float Uf[9], Vf[9], sf[3];
+    const bool ok = proper_svd3_t<float>(A, Uf, Vf, sf);
+    proper_svd3_t<double>(A, U, V, s, Vf, kJacobiPolishF64);
+#endif
     *T = s[0] + s[1] + s[2];
 #pragma unroll
     for (int i = 0; i < 3; ++i)

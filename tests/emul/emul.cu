@@ -289,6 +289,19 @@ void emul_rad_to_deg(const float* rad, long n, float* out) {
     for (long i = 0; i < n; ++i) out[i] = rad_to_deg_ref(rad[i]);
 }
 
+// K2L per-sample set-up as the kernels run it (fp32 Jacobi + fp64 polishing) next to seven fp64 sweeps from scratch
+void emul_laplace_setup(const float* A, long n, float* Rs, double* T, double* Rs_f64, double* T_f64) {
+    for (long i = 0; i < n; ++i) {
+        laplace_setup(A + 9 * i, Rs + 9 * i, T + i);
+        double U[9], V[9], s[3];
+        proper_svd3_t<double>(A + 9 * i, U, V, s);
+        T_f64[i] = s[0] + s[1] + s[2];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                Rs_f64[9 * i + 3 * r + c] = U[3 * r] * V[3 * c] + U[3 * r + 1] * V[3 * c + 1] + U[3 * r + 2] * V[3 * c + 2];
+    }
+}
+
 // K2L with the kernel's two decompositions: L = 1 (one thread walks the grid in order) and
 // L = 32 (lane l takes points l, l+32, ...; partials rebased to the common minimum, butterfly-merged)
 void emul_laplace(const float* A, const float* Rgt, long n, const float* grid, int N, int L,

@@ -168,6 +168,35 @@ def run_laplace(emul, A, R, grid, L):
     return o
 
 
+def test_laplace_setup_mixed_precision(emul):
+    """K2L's per-sample set-up (mode R*, T = s1 + s2 + s3 signed) starts its fp64 iteration from the V of the fp32
+    one (Newton-Schulz step, two polishing sweeps).  Against seven fp64 sweeps from scratch: T to 2e-12 relative --
+    it feeds the fp64 cancellation T - <A,R_gt> -- and R* to fp32 rounding, on random, scaled, ill-conditioned
+    (cond 1e3 and 1e6), nearly rank-deficient, nearly degenerate and negative-determinant matrices."""
+    rng = np.random.default_rng(5)
+    n = 4000
+    kinds = []
+    for kind in range(8):
+        A = rng.standard_normal((n, 3, 3)).astype(np.float32)
+        if kind == 1: A *= 50
+        if kind == 2: A *= 1e-3
+        if kind == 3: A[:, :, 2] *= 1e-3; A *= 10
+        if kind == 4: A[:, :, 2] *= 1e-6; A *= 10
+        if kind == 5: A[:, :, 1] = A[:, :, 0] * (1 + 1e-4 * rng.standard_normal((n, 3))).astype(np.float32); A *= 5
+        if kind == 6: A = (3 * np.eye(3) + 1e-5 * rng.standard_normal((n, 3, 3))).astype(np.float32)
+        if kind == 7: A = (np.diag([2, 2, -2]) + 0.1 * rng.standard_normal((n, 3, 3))).astype(np.float32)
+        kinds.append(A)
+    A = np.ascontiguousarray(np.concatenate(kinds).reshape(-1, 9))
+    m = len(A)
+    Rs, T = np.empty((m, 9), np.float32), np.empty(m, np.float64)
+    Rs64, T64 = np.empty((m, 9), np.float64), np.empty(m, np.float64)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    emul.emul_laplace_setup(P(A), ctypes.c_long(m), P(Rs), P(T), P(Rs64), P(T64))
+    assert np.isfinite(T).all() and np.isfinite(Rs).all()
+    assert (np.abs(T - T64) <= 2e-12 * np.abs(T64) + 1e-300).all()
+    assert np.abs(Rs - Rs64).max() < 6e-8
+
+
 def test_laplace_against_golden(emul, golden):
     """K2L arithmetic (fp64 per-sample set-up, two-level fp32 grid sums) in both decompositions the
     kernel uses: parity with the reference's fp32 output, closer to exact arithmetic than the
