@@ -505,9 +505,14 @@ fisher_fused_kernel(FisherArgs p) {
                 t += __shfl_xor_sync(kFull, t, 4);
                 t += __shfl_xor_sync(kFull, t, 2);
                 t += __shfl_xor_sync(kFull, t, 1);
+                // the slot by its shared-window address off desc_s (a generic pointer into ws.a makes the four lanes
+                // re-derive the window base -- two S2R and ten more instructions -- once per rotation)
+                const unsigned slot_s = desc_s - (unsigned)(offsetof(WarpScratch, desc) - offsetof(WarpScratch, a))
+                                      + 4u * (unsigned)(j * 9 + 4 + (lane_r >> 3));
                 if ((lane_r & 7) == 0) {
-                    float* slot = ws.a + j * 9 + 4 + (lane_r >> 3);
-                    *slot = t - *slot;
+                    float corr;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(corr) : "r"(slot_s) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" : : "r"(slot_s), "f"(t - corr) : "memory");
                 }
             }
         }
